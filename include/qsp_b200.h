@@ -1,0 +1,132 @@
+/* qsp_b200 -- C ABI of the B200-native sequential MPS-encoding path.
+ *
+ * Drop-in boundary for mohsin-0/qsp's `MPSPreparation.sequential_unitary_circuit`
+ * (qsp/tsp.py:79-149 -> qsp/sequential/sequential.py:19-102 -> qsp/sequential/core.py and
+ * qsp/tsp_helper_routines/helper_routines.py:29-73).  The reference has no FFI layer of its
+ * own (it is pure Python on top of quimb); these entry points are what a binding for this
+ * path would call -- INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch tensors in the python
+ *    host); nothing is allocated behind the caller's back: scratch comes from `work`,
+ *    sized by the matching *_workspace_bytes() query;
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per
+ *    stream, one device per call;
+ *  - complex128 = two doubles (re, im);
+ *  - a batch of B independent MPS of L sites is stored as mps[B][L][D][2][D]: element
+ *    (l, p, r) of a site at (l*2+p)*D + r, D = padded bond; the live extent of bond j of
+ *    instance b is bonds[b][j] (int32, j = 0..L, bonds[.][0] = bonds[.][L] = 1).  Nothing
+ *    outside the live extent is read; padding is never initialised;
+ *  - gates: G[..][L][4][4] row-major, exactly the matrices the reference keeps in
+ *    Gs[i].data (core.py:46,71-73,105-107); a one-qubit gate sits in the top-left 2x2
+ *    block.  kind[..][L]: 2 = two-qubit gate on (it, it+1), 1 = one-qubit gate on it (the
+ *    site closes a segment, core.py:243-270);
+ *  - status[B] is OR-ed with QSP_ST_* bits; the caller zeroes it.
+ *  - return value: 0 on success, a QSP_ERR_* code otherwise (nothing was launched when
+ *    the code is QSP_ERR_UNSUPPORTED / QSP_ERR_WORKSPACE / QSP_ERR_ARG).
+ */
+#ifndef QSP_B200_H
+#define QSP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  double re, im;
+} qsp_c128;
+
+#define QSP_OK 0
+#define QSP_ERR_ARG 1         /* null pointer / non-positive size */
+#define QSP_ERR_UNSUPPORTED 2 /* bond dimension too large for this build's shared-memory kernels */
+#define QSP_ERR_WORKSPACE 3   /* work_bytes smaller than the query says */
+#define QSP_ERR_CUDA 4        /* a launch failed; see qsp_last_cuda_error() */
+
+#define QSP_ST_JACOBI_NOCONV 1
+#define QSP_ST_BOND_OVERFLOW 2
+#define QSP_ST_NONUNITARY 4
+#define QSP_ST_DEGENERATE 8
+#define QSP_ST_BADNORM 16
+
+int qsp_version(void);
+/* 1 when the library was built for a CUDA device, 0 for the CPU emulation used by the
+ * test-suite (tests/emu) -- the python package refuses to run on the latter. */
+int qsp_is_device_build(void);
+const char* qsp_last_cuda_error(void);
+/* number of kernel launches issued by this library since load (bench.py: gpu_launches) */
+long long qsp_launch_count(void);
+
+/* quimb MPS.left_canonize() in place (first half of `compress`, tsp.py:72, core.py:17,
+ * sequential.py:54,57).  R has a non-negative real diagonal (quimb's stabilised QR). */
+int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* stream);
+
+/* quimb MPS.right_compress(max_bond, cutoff, cutoff_mode='rel') on a LEFT-canonical input:
+ * right-to-left truncating SVD sweep (second half of `compress`).  max_bond = 0: cutoff
+ * only.  normalize != 0: the orthogonality centre (site 0) is divided by its norm
+ * (right_canonize(normalize=True), sequential.py:53,56).  svals (optional): the nsv
+ * largest singular values seen at each bond, svals[b][i-1][0..nsv) for the bond between
+ * sites i-1 and i.  amp0 (optional): <0...0|out>/||out||, i.e. norm_mps_ovrlap(out,
+ * cl_zero_mps(L)) (helper_routines.py:65-73, sequential.py:60). */
+size_t qsp_right_compress_workspace_bytes(int B, int L, int D_in, int D_out);
+int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, int D_in, qsp_c128* out, int32_t* bonds_out,
+                       int D_out, int B, int L, int max_bond, double cutoff, int normalize, double* svals, int nsv,
+                       qsp_c128* amp0, int32_t* status, void* work, size_t work_bytes, void* stream);
+
+/* generate_unitaries (core.py:25-123) on the D<=2 right-canonical, normalised MPS
+ * d2[B][L][2][2][2] (gauge-fixed in place), with the deterministic 'canonical' completion
+ *  in place of scipy.linalg.null_space. */
+int qsp_generate_unitaries(qsp_c128* d2, const int32_t* d2_bonds, int B, int L, qsp_c128* G, int32_t* kind,
+                           int32_t* status, void* stream);
+
+/* apply_inverse_unitary_layer_on_wfn (core.py:224-240) on a LEFT-canonical MPS, exact
+ * (bonds double inside a segment, D_out >= 2*max bond); the result is left canonical. */
+int qsp_apply_inverse_layer(const qsp_c128* in, const int32_t* bonds_in, int D_in, const qsp_c128* G,
+                            const int32_t* kind, qsp_c128* out, int32_t* bonds_out, int D_out, int B, int L,
+                            int32_t* status, void* stream);
+/* the gate application of apply_unitary_layer_on_wfn (core.py:126-138) on a
+ * RIGHT-canonical MPS, exact; the `compress('right')` of core.py:140 is
+ * qsp_left_canonize + qsp_right_compress on the result. */
+int qsp_apply_forward_layer(const qsp_c128* in, const int32_t* bonds_in, int D_in, const qsp_c128* G,
+                            const int32_t* kind, qsp_c128* out, int32_t* bonds_out, int D_out, int B, int L,
+                            int32_t* status, void* stream);
+
+/* sum_x a(x) conj(b(x)) -- the numerator of norm_mps_ovrlap(a, b) (helper_routines.py:69). */
+size_t qsp_overlap_workspace_bytes(int B, int L, int D_a, int D_b);
+int qsp_overlap(const qsp_c128* a, const int32_t* bonds_a, int D_a, const qsp_c128* b, const int32_t* bonds_b,
+                int D_b, int B, int L, qsp_c128* result, void* work, size_t work_bytes, void* stream);
+
+/* MPSPreparation.__init__ + the first lines of sequential_unitary_circuit (tsp.py:63-77,
+ * sequential.py:38-40): normalise, compress('right'), right_canonize(normalize=True).
+ * In place on mps/bonds; `tmp` has the size of mps. */
+size_t qsp_prepare_target_workspace_bytes(int B, int L, int D);
+int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, int D, double cutoff, int32_t* status,
+                       void* work, size_t work_bytes, void* stream);
+
+/* The whole layer loop of sequential_unitary_circuit (sequential.py:42-85) for a batch.
+ *   target / target_bonds : right-canonical normalised MPS (qsp_prepare_target output), D-padded;
+ *                           every bond must stay <= D at every layer start (with
+ *                           max_bond = 0 the caller pads for the doubling: D >= min(chi*2^layers, 2^(L/2)))
+ *   max_bond              : do_compression ? max_bond_dim : 0
+ *   flags                 : QSP_FLAG_*
+ * Outputs (layer-major so that every layer is one contiguous batch slab):
+ *   overlaps[layers][B]      encoded-state overlaps <target|U_0..U_it|0> at it % overlaps_gap == 0
+ *                            and at the last layer (sequential.py:67-70); NaN elsewhere
+ *   dis_overlaps[layers][B]  norm_mps_ovrlap(disentangled mps, |0..0>)  (sequential.py:60)
+ *   G[layers][B][L][4][4], kind[layers][B][L]
+ *   d2_svals[layers][B][L-1][2]  the two largest singular values at every bond of the D=2 truncation
+ *   final_mps / final_bonds  (optional) the disentangled MPS after the last layer, D-padded
+ */
+#define QSP_FLAG_SECOND_PASS 1 /* also run the trailing cutoff-only compress() of sequential.py:56-57 */
+#define QSP_FLAG_NO_ENCODED 2  /* skip the encoded-state overlaps (overlaps[] stays NaN) */
+size_t qsp_seq_prepare_workspace_bytes(int B, int L, int D, int layers, int max_bond, int flags);
+int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bonds, int B, int L, int D, int layers,
+                    int max_bond, double cutoff, int overlaps_gap, int flags, qsp_c128* overlaps,
+                    qsp_c128* dis_overlaps, qsp_c128* G, int32_t* kind, double* d2_svals, qsp_c128* final_mps,
+                    int32_t* final_bonds, int32_t* status, void* work, size_t work_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,472 @@
+// C ABI of libqsp_b200.so (include/qsp_b200.h): launch configuration, workspace
+// partitioning and the batched layer loop of sequential_unitary_circuit
+// (qsp/sequential/sequential.py:42-85).  Host-side only; all arithmetic is in the kernels.
+#include "../../include/qsp_b200.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "qsp_sweeps.cuh"
+#include "qsp_unitaries.cuh"
+
+#ifdef QSP_EMU
+thread_local emu::Block* emu::g_blk = nullptr;
+thread_local dim3 emu::g_threadIdx, emu::g_blockIdx, emu::g_blockDim, emu::g_gridDim;
+#endif
+
+static long long g_launches = 0;
+static char g_err[256] = "";
+
+// ------------------------------------------------------------------------------------
+// device facts
+// ------------------------------------------------------------------------------------
+struct DevInfo {
+  int sms;
+  size_t max_smem;  // per block, opt-in
+};
+static DevInfo dev_info() {
+  DevInfo d;
+#ifdef QSP_EMU
+  d.sms = 2;
+  d.max_smem = 227 * 1024;
+#else
+  int dev = 0, v = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  d.sms = v > 0 ? v : 148;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  d.max_smem = v > 0 ? (size_t)v : (size_t)227 * 1024;
+#endif
+  return d;
+}
+
+#ifdef QSP_EMU
+#define QSP_PREP_KERNEL(kernel, smem) (0)
+static int blocks_per_sm(const void*, int, size_t) { return 1; }
+static int check_launch() { return QSP_OK; }
+static void dev_fill_nan(qsp_c128* p, long n, qsp_stream_t) {
+  for (long i = 0; i < n; ++i) p[i].re = p[i].im = NAN;
+}
+static void dev_copy(void* dst, const void* src, size_t bytes, qsp_stream_t) { memcpy(dst, src, bytes); }
+#else
+#define QSP_PREP_KERNEL(kernel, smem) \
+  cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))
+static int blocks_per_sm(const void* kernel, int nt, size_t smem) {
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, nt, smem);
+  return n > 0 ? n : 1;
+}
+static int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s", cudaGetErrorString(e));
+    return QSP_ERR_CUDA;
+  }
+  return QSP_OK;
+}
+__global__ void k_fill_nan(cplx* p, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = cmake(nan(""), nan(""));
+}
+static void dev_fill_nan(qsp_c128* p, long n, qsp_stream_t s) {
+  if (n <= 0) return;
+  k_fill_nan<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((cplx*)p, n);
+  ++g_launches;
+}
+static void dev_copy(void* dst, const void* src, size_t bytes, qsp_stream_t s) {
+  cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
+}
+#endif
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+static int grid_for(int B, int per_sm, const DevInfo& d) {
+  long g = (long)d.sms * per_sm;
+#ifdef QSP_EMU
+  g = 2;
+#endif
+  return (int)(B < g ? B : g);
+}
+
+// ------------------------------------------------------------------------------------
+// launch plans
+// ------------------------------------------------------------------------------------
+struct LCanonPlan {
+  int nt;
+  size_t smem;
+};
+static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
+  p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : 256);
+  p->smem = lcanon_smem_bytes(D, p->nt);
+  return p->smem <= d.max_smem;
+}
+
+struct RCompressPlan {
+  int nt, tpp;
+  int jac_elems;
+  size_t smem;
+};
+static bool plan_rcompress(int Din, int Dout, const DevInfo& d, RCompressPlan* p) {
+  const int dm = imax(Din / 2, Dout);
+  p->nt = dm >= 48 ? 512 : (dm >= 16 ? 256 : (dm >= 4 ? 128 : 64));
+  int tpp = 32;
+  while (tpp > 2 && p->nt / tpp < imin(Dout, Din)) tpp >>= 1;  // >= one team per pair when possible
+  p->tpp = tpp;
+  // largest Jacobi working set: mode R (b <= c): 2Dout x 2Dout; mode C (c < b): c x (b + c)
+  long needR = 4L * Dout * Dout;
+  long cmax = imin(2 * Dout, Din - 1);
+  long needC = cmax > 0 ? cmax * ((long)Din + cmax) : 0;
+  long need = needR > needC ? needR : needC;
+  size_t fixed = rcompress_smem_bytes(0, Dout, p->nt) - qsp_gemm_smem_bytes(p->nt);
+  long budget = ((long)d.max_smem - (long)fixed) / (long)sizeof(cplx);
+  long gem = (long)(qsp_gemm_smem_bytes(p->nt) / sizeof(cplx));
+  if (budget < gem) return false;
+  long je = need < budget ? need : budget;
+  // at least two rows of the longest possible row must fit
+  long maxlen = imax(2 * Dout, Din + (int)cmax);
+  if (je < 2 * maxlen) return false;
+  p->jac_elems = (int)je;
+  p->smem = rcompress_smem_bytes(p->jac_elems, Dout, p->nt);
+  return p->smem <= d.max_smem;
+}
+
+// ------------------------------------------------------------------------------------
+// unit-level entry points
+// ------------------------------------------------------------------------------------
+extern "C" int qsp_version(void) { return 1; }
+extern "C" int qsp_is_device_build(void) {
+#ifdef QSP_EMU
+  return 0;
+#else
+  return 1;
+#endif
+}
+extern "C" const char* qsp_last_cuda_error(void) { return g_err; }
+extern "C" long long qsp_launch_count(void) { return g_launches; }
+
+extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* stream) {
+  if (!mps || !bonds || B <= 0 || L <= 0 || D <= 0) return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  LCanonPlan p;
+  if (!plan_lcanon(D, d, &p)) return QSP_ERR_UNSUPPORTED;
+  QSP_PREP_KERNEL(k_left_canon, p.smem);
+  int grid = grid_for(B, blocks_per_sm((const void*)k_left_canon, p.nt, p.smem), d);
+  QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, D, status);
+  ++g_launches;
+  return check_launch();
+}
+
+static int rcompress_grid(int B, const RCompressPlan& p, const DevInfo& d) {
+  return grid_for(B, blocks_per_sm((const void*)k_right_compress, p.nt, p.smem), d);
+}
+
+extern "C" size_t qsp_right_compress_workspace_bytes(int B, int L, int D_in, int D_out) {
+  (void)L;
+  DevInfo d = dev_info();
+  RCompressPlan p;
+  if (!plan_rcompress(D_in, D_out, d, &p)) return 0;
+#ifndef QSP_EMU
+  QSP_PREP_KERNEL(k_right_compress, p.smem);
+#endif
+  int grid = rcompress_grid(B, p, d);
+  return align_up((size_t)grid * rcompress_work_elems(D_in, D_out) * sizeof(cplx));
+}
+
+extern "C" int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, int D_in, qsp_c128* out,
+                                  int32_t* bonds_out, int D_out, int B, int L, int max_bond, double cutoff,
+                                  int normalize, double* svals, int nsv, qsp_c128* amp0, int32_t* status, void* work,
+                                  size_t work_bytes, void* stream) {
+  if (!in || !bonds_in || !out || !bonds_out || !work || B <= 0 || L <= 0 || D_in <= 0 || D_out <= 0)
+    return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  RCompressPlan p;
+  if (!plan_rcompress(D_in, D_out, d, &p)) return QSP_ERR_UNSUPPORTED;
+  QSP_PREP_KERNEL(k_right_compress, p.smem);
+  int grid = rcompress_grid(B, p, d);
+  long stride = rcompress_work_elems(D_in, D_out);
+  if (work_bytes < (size_t)grid * stride * sizeof(cplx)) return QSP_ERR_WORKSPACE;
+  RCompressArgs a;
+  a.in = (const cplx*)in;
+  a.bonds_in = bonds_in;
+  a.Din = D_in;
+  a.out = (cplx*)out;
+  a.bonds_out = bonds_out;
+  a.Dout = D_out;
+  a.B = B;
+  a.L = L;
+  a.max_bond = max_bond;
+  a.cutoff = cutoff;
+  a.normalize = normalize;
+  a.svals = svals;
+  a.nsv = nsv;
+  a.amp0 = (cplx*)amp0;
+  a.status = status;
+  a.work = (cplx*)work;
+  a.work_stride = stride;
+  a.cap_rows_elems = p.jac_elems;
+  a.tpp = p.tpp;
+  a.max_sweeps = 60;
+  QSP_LAUNCH(k_right_compress, grid, p.nt, p.smem, (qsp_stream_t)stream, a);
+  ++g_launches;
+  return check_launch();
+}
+
+extern "C" int qsp_generate_unitaries(qsp_c128* d2, const int32_t* d2_bonds, int B, int L, qsp_c128* G,
+                                      int32_t* kind, int32_t* status, void* stream) {
+  if (!d2 || !d2_bonds || !G || !kind || B <= 0 || L <= 0) return QSP_ERR_ARG;
+  const int nt = 64;
+  QSP_LAUNCH(k_unitaries, (B + nt - 1) / nt, nt, 0, (qsp_stream_t)stream, (cplx*)d2, d2_bonds, B, L, (cplx*)G, kind,
+             status);
+  ++g_launches;
+  return check_launch();
+}
+
+extern "C" int qsp_apply_inverse_layer(const qsp_c128* in, const int32_t* bonds_in, int D_in, const qsp_c128* G,
+                                       const int32_t* kind, qsp_c128* out, int32_t* bonds_out, int D_out, int B,
+                                       int L, int32_t* status, void* stream) {
+  if (!in || !bonds_in || !G || !kind || !out || !bonds_out || B <= 0 || L <= 0) return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  int grid = grid_for(B, 4, d);
+  QSP_LAUNCH(k_expand_inverse, grid, 256, 0, (qsp_stream_t)stream, (const cplx*)in, bonds_in, D_in, (const cplx*)G,
+             kind, (cplx*)out, bonds_out, D_out, B, L, status);
+  ++g_launches;
+  return check_launch();
+}
+
+extern "C" int qsp_apply_forward_layer(const qsp_c128* in, const int32_t* bonds_in, int D_in, const qsp_c128* G,
+                                       const int32_t* kind, qsp_c128* out, int32_t* bonds_out, int D_out, int B,
+                                       int L, int32_t* status, void* stream) {
+  if (!in || !bonds_in || !G || !kind || !out || !bonds_out || B <= 0 || L <= 0) return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  int grid = grid_for(B, 4, d);
+  QSP_LAUNCH(k_expand_forward, grid, 256, 0, (qsp_stream_t)stream, (const cplx*)in, bonds_in, D_in, (const cplx*)G,
+             kind, (cplx*)out, bonds_out, D_out, B, L, status);
+  ++g_launches;
+  return check_launch();
+}
+
+static const int kOverlapNT = 256;
+extern "C" size_t qsp_overlap_workspace_bytes(int B, int L, int D_a, int D_b) {
+  (void)L;
+  DevInfo d = dev_info();
+  int grid = grid_for(B, 2, d);
+  return align_up((size_t)grid * overlap_work_elems(D_a, D_b) * sizeof(cplx));
+}
+extern "C" int qsp_overlap(const qsp_c128* a, const int32_t* bonds_a, int D_a, const qsp_c128* b,
+                           const int32_t* bonds_b, int D_b, int B, int L, qsp_c128* result, void* work,
+                           size_t work_bytes, void* stream) {
+  if (!a || !bonds_a || !b || !bonds_b || !result || !work || B <= 0 || L <= 0) return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  int grid = grid_for(B, 2, d);
+  long stride = overlap_work_elems(D_a, D_b);
+  if (work_bytes < (size_t)grid * stride * sizeof(cplx)) return QSP_ERR_WORKSPACE;
+  size_t smem = qsp_gemm_smem_bytes(kOverlapNT) + 64;
+  QSP_LAUNCH(k_overlap, grid, kOverlapNT, smem, (qsp_stream_t)stream, (const cplx*)a, bonds_a, D_a, (const cplx*)b,
+             bonds_b, D_b, B, L, (cplx*)result, (cplx*)work, stride);
+  ++g_launches;
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------
+// input pipeline: MPSPreparation.__init__ + sequential.py:38-40
+// ------------------------------------------------------------------------------------
+static size_t mps_bytes(int B, int L, int D) { return align_up((size_t)B * L * D * 2 * D * sizeof(cplx)); }
+static size_t bonds_bytes(int B, int L) { return align_up((size_t)B * (L + 1) * sizeof(int32_t)); }
+
+extern "C" size_t qsp_prepare_target_workspace_bytes(int B, int L, int D) {
+  size_t w = qsp_right_compress_workspace_bytes(B, L, D, D);
+  if (w == 0) return 0;
+  return mps_bytes(B, L, D) + bonds_bytes(B, L) + w;
+}
+extern "C" int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, int D, double cutoff, int32_t* status,
+                                  void* work, size_t work_bytes, void* stream) {
+  if (!mps || !bonds || !work) return QSP_ERR_ARG;
+  size_t need = qsp_prepare_target_workspace_bytes(B, L, D);
+  if (need == 0) return QSP_ERR_UNSUPPORTED;
+  if (work_bytes < need) return QSP_ERR_WORKSPACE;
+  char* w = (char*)work;
+  qsp_c128* tmp = (qsp_c128*)w;
+  w += mps_bytes(B, L, D);
+  int32_t* tb = (int32_t*)w;
+  w += bonds_bytes(B, L);
+  size_t wb = qsp_right_compress_workspace_bytes(B, L, D, D);
+  int rc = qsp_left_canonize(mps, bonds, B, L, D, status, stream);
+  if (rc) return rc;
+  rc = qsp_right_compress(mps, bonds, D, tmp, tb, D, B, L, 0, cutoff, 1, nullptr, 0, nullptr, status, w, wb, stream);
+  if (rc) return rc;
+  dev_copy(mps, tmp, (size_t)B * L * D * 2 * D * sizeof(cplx), (qsp_stream_t)stream);
+  dev_copy(bonds, tb, (size_t)B * (L + 1) * sizeof(int32_t), (qsp_stream_t)stream);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------
+// the layer loop
+// ------------------------------------------------------------------------------------
+struct SeqPlan {
+  int De;  // padded bond of the encoded state
+  size_t off_psi, off_psib, off_psi2, off_psi2b, off_d2, off_d2b, off_tmp, off_tmpb;
+  size_t off_enc, off_encb, off_enc2, off_enc2b, off_zero, off_zerob, off_scratch;
+  size_t scratch_bytes, total;
+  bool ok;
+};
+static int enc_pad(int L, int layers) {
+  int cap = L / 2;
+  int e = layers < cap ? layers : cap;
+  if (e > 20) e = 20;
+  return 1 << e;
+}
+static SeqPlan plan_seq(int B, int L, int D, int layers, int max_bond, int flags) {
+  (void)max_bond;
+  SeqPlan p;
+  memset(&p, 0, sizeof(p));
+  p.ok = true;
+  const bool enc = !(flags & QSP_FLAG_NO_ENCODED);
+  const bool second = (flags & QSP_FLAG_SECOND_PASS) != 0;
+  p.De = enc ? enc_pad(L, layers) : 1;
+  size_t o = 0;
+  p.off_psi = o, o += mps_bytes(B, L, D);
+  p.off_psib = o, o += bonds_bytes(B, L);
+  p.off_psi2 = o, o += mps_bytes(B, L, 2 * D);
+  p.off_psi2b = o, o += bonds_bytes(B, L);
+  p.off_d2 = o, o += mps_bytes(B, L, 2);
+  p.off_d2b = o, o += bonds_bytes(B, L);
+  if (second) {
+    p.off_tmp = o, o += mps_bytes(B, L, D);
+    p.off_tmpb = o, o += bonds_bytes(B, L);
+  }
+  size_t s = 0, t;
+  DevInfo d = dev_info();
+  LCanonPlan lp;
+  if (!plan_lcanon(D, d, &lp)) p.ok = false;
+  t = qsp_right_compress_workspace_bytes(B, L, D, 2);
+  if (!t) p.ok = false;
+  s = t > s ? t : s;
+  t = qsp_right_compress_workspace_bytes(B, L, 2 * D, D);
+  if (!t) p.ok = false;
+  s = t > s ? t : s;
+  if (second) {
+    t = qsp_right_compress_workspace_bytes(B, L, D, D);
+    if (!t) p.ok = false;
+    s = t > s ? t : s;
+  }
+  if (enc) {
+    p.off_enc = o, o += mps_bytes(B, L, p.De);
+    p.off_encb = o, o += bonds_bytes(B, L);
+    p.off_enc2 = o, o += mps_bytes(B, L, 2 * p.De);
+    p.off_enc2b = o, o += bonds_bytes(B, L);
+    if (!plan_lcanon(2 * p.De, d, &lp)) p.ok = false;
+    t = qsp_right_compress_workspace_bytes(B, L, 2 * p.De, p.De);
+    if (!t) p.ok = false;
+    s = t > s ? t : s;
+    t = qsp_overlap_workspace_bytes(B, L, p.De, D);
+    s = t > s ? t : s;
+  }
+  p.off_scratch = o;
+  p.scratch_bytes = s;
+  p.total = o + s;
+  return p;
+}
+
+extern "C" size_t qsp_seq_prepare_workspace_bytes(int B, int L, int D, int layers, int max_bond, int flags) {
+  if (B <= 0 || L <= 0 || D <= 0 || layers <= 0) return 0;
+  SeqPlan p = plan_seq(B, L, D, layers, max_bond, flags);
+  return p.ok ? p.total : 0;
+}
+
+// zero state |0...0> into enc (pad De): helper kernel
+__global__ void k_zero_state(cplx* mps, int32_t* bonds, int B, int L, int D) {
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * L) return;
+  int inst = (int)(idx / L), i = (int)(idx - (long)inst * L);
+  cplx* a = mps + idx * ((long)D * 2 * D);
+  a[0] = cmake(1.0, 0.0);      // (l=0,p=0,r=0)
+  a[(long)D] = cmake(0.0, 0.0);  // (l=0,p=1,r=0)
+  bonds[(long)inst * (L + 1) + i] = 1;
+  if (i == L - 1) bonds[(long)inst * (L + 1) + L] = 1;
+}
+
+extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bonds, int B, int L, int D, int layers,
+                               int max_bond, double cutoff, int overlaps_gap, int flags, qsp_c128* overlaps,
+                               qsp_c128* dis_overlaps, qsp_c128* G, int32_t* kind, double* d2_svals,
+                               qsp_c128* final_mps, int32_t* final_bonds, int32_t* status, void* work,
+                               size_t work_bytes, void* stream) {
+  if (!target || !target_bonds || !dis_overlaps || !G || !kind || !status || !work) return QSP_ERR_ARG;
+  if (B <= 0 || L <= 0 || D <= 0 || layers <= 0 || overlaps_gap <= 0) return QSP_ERR_ARG;
+  if (max_bond > D) return QSP_ERR_ARG;
+  SeqPlan p = plan_seq(B, L, D, layers, max_bond, flags);
+  if (!p.ok) return QSP_ERR_UNSUPPORTED;
+  if (work_bytes < p.total) return QSP_ERR_WORKSPACE;
+  const bool enc_on = !(flags & QSP_FLAG_NO_ENCODED) && overlaps;
+  const bool second = (flags & QSP_FLAG_SECOND_PASS) != 0 && max_bond > 0;
+  qsp_stream_t st = (qsp_stream_t)stream;
+  char* w = (char*)work;
+  qsp_c128* psi = (qsp_c128*)(w + p.off_psi);
+  int32_t* psib = (int32_t*)(w + p.off_psib);
+  qsp_c128* psi2 = (qsp_c128*)(w + p.off_psi2);
+  int32_t* psi2b = (int32_t*)(w + p.off_psi2b);
+  qsp_c128* d2 = (qsp_c128*)(w + p.off_d2);
+  int32_t* d2b = (int32_t*)(w + p.off_d2b);
+  qsp_c128* tmp = (qsp_c128*)(w + p.off_tmp);
+  int32_t* tmpb = (int32_t*)(w + p.off_tmpb);
+  qsp_c128* enc = (qsp_c128*)(w + p.off_enc);
+  int32_t* encb = (int32_t*)(w + p.off_encb);
+  qsp_c128* enc2 = (qsp_c128*)(w + p.off_enc2);
+  int32_t* enc2b = (int32_t*)(w + p.off_enc2b);
+  void* scratch = w + p.off_scratch;
+  const size_t sb = p.scratch_bytes;
+  const int De = p.De;
+  int rc;
+
+  dev_copy(psi, target, (size_t)B * L * D * 2 * D * sizeof(cplx), st);
+  dev_copy(psib, target_bonds, (size_t)B * (L + 1) * sizeof(int32_t), st);
+  if (overlaps) dev_fill_nan(overlaps, (long)layers * B, st);
+
+  for (int it = 0; it < layers; ++it) {
+    qsp_c128* Git = G + (size_t)it * B * L * 16;
+    int32_t* kit = kind + (size_t)it * B * L;
+    double* sv = d2_svals ? d2_svals + (size_t)it * B * (L - 1) * 2 : nullptr;
+    // generate_bond_d_unitary (core.py:12-22): compress('right', max_bond=2) = left sweep + truncating right sweep
+    if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, stream))) return rc;
+    if ((rc = qsp_right_compress(psi, psib, D, d2, d2b, 2, B, L, 2, cutoff, 1, sv, 2, nullptr, status, scratch, sb,
+                                 stream)))
+      return rc;
+    if ((rc = qsp_generate_unitaries(d2, d2b, B, L, Git, kit, status, stream))) return rc;
+    // apply_inverse_unitary_layer_on_wfn (sequential.py:51) on the left-canonical psi: exact, left canonical
+    if ((rc = qsp_apply_inverse_layer(psi, psib, D, Git, kit, psi2, psi2b, 2 * D, B, L, status, stream))) return rc;
+    // sequential.py:52-57: [right_canonize; compress('right', max_bond)] ; right_canonize(normalize) ; compress()
+    qsp_c128* amp = dis_overlaps + (size_t)it * B;
+    if ((rc = qsp_right_compress(psi2, psi2b, 2 * D, psi, psib, D, B, L, max_bond, cutoff, 1, nullptr, 0,
+                                 second ? nullptr : amp, status, scratch, sb, stream)))
+      return rc;
+    if (second) {
+      if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, stream))) return rc;
+      if ((rc = qsp_right_compress(psi, psib, D, tmp, tmpb, D, B, L, 0, cutoff, 1, nullptr, 0, amp, status, scratch,
+                                   sb, stream)))
+        return rc;
+      dev_copy(psi, tmp, (size_t)B * L * D * 2 * D * sizeof(cplx), st);
+      dev_copy(psib, tmpb, (size_t)B * (L + 1) * sizeof(int32_t), st);
+    }
+    // sequential.py:67-70: encoded state U_0 .. U_it |0..0> and its overlap with the target
+    if (enc_on && (it % overlaps_gap == 0 || it + 1 == layers)) {
+      long n = (long)B * L;
+      QSP_LAUNCH(k_zero_state, (unsigned)((n + 127) / 128), 128, 0, st, (cplx*)enc, encb, B, L, De);
+      ++g_launches;
+      for (int k = it; k >= 0; --k) {
+        const qsp_c128* Gk = G + (size_t)k * B * L * 16;
+        const int32_t* kk = kind + (size_t)k * B * L;
+        if ((rc = qsp_apply_forward_layer(enc, encb, De, Gk, kk, enc2, enc2b, 2 * De, B, L, status, stream)))
+          return rc;
+        if ((rc = qsp_left_canonize(enc2, enc2b, B, L, 2 * De, status, stream))) return rc;
+        if ((rc = qsp_right_compress(enc2, enc2b, 2 * De, enc, encb, De, B, L, 0, cutoff, k == 0 ? 1 : 0, nullptr, 0,
+                                     nullptr, status, scratch, sb, stream)))
+          return rc;
+      }
+      if ((rc = qsp_overlap(enc, encb, De, target, target_bonds, D, B, L, overlaps + (size_t)it * B, scratch, sb,
+                            stream)))
+        return rc;
+    }
+  }
+  if (final_mps) dev_copy(final_mps, psi, (size_t)B * L * D * 2 * D * sizeof(cplx), st);
+  if (final_bonds) dev_copy(final_bonds, psib, (size_t)B * (L + 1) * sizeof(int32_t), st);
+  return check_launch();
+}

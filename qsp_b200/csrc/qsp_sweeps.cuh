@@ -1,0 +1,456 @@
+// The two canonisation sweeps of the sequential MPS-encoding path, batched over
+// independent MPS instances: one persistent CTA walks one instance along the chain
+// (sites are strictly sequential), instances are strided over the grid.
+//
+//   k_left_canon      quimb MPS.left_canonize()  (first half of `compress`; tsp.py:72,
+//                     core.py:17, sequential.py:54,57)  Householder QR of the
+//                     (2a x b) site matrix held in shared memory, R carried to the next
+//                     site through a fused R*A GEMM.
+//   k_right_compress  quimb MPS.right_compress() on a LEFT-canonical input (second half of
+//                     `compress`): per bond a one-sided Jacobi SVD of the (b x 2r') site
+//                     matrix, rel. cutoff + max_bond truncation, A[i] <- Vh,
+//                     A[i-1] <- A[i-1] (U s).  (T1 is an isometry after the left sweep, so
+//                     the reference's QR(T1)/LQ(T2) reduction is the identity on T1 and
+//                     the SVD of T2 alone gives the same factors -- DESIGN.md, I1.)
+//
+// MPS layout in HBM: [B][L][D][2][D] complex128, element (l,p,r) of a site at
+// (l*2+p)*D + r; the live extent of every bond is in bonds[B][L+1] (int32).  Nothing
+// outside the live extent is ever read.
+#pragma once
+#include "qsp_common.cuh"
+#include "qsp_gemm.cuh"
+#include "qsp_jacobi.cuh"
+
+// ----------------------------------------------------------------------------------
+// left canonisation
+// ----------------------------------------------------------------------------------
+__host__ __device__ inline size_t lcanon_smem_bytes(int Dm, int nt) {
+  size_t s = 0;
+  s += (size_t)Dm * (2 * Dm + 1) * sizeof(cplx);  // S
+  s += (size_t)Dm * Dm * sizeof(cplx);            // R
+  s += (size_t)Dm * sizeof(cplx);                 // tau
+  s += (size_t)Dm * sizeof(double);               // beta
+  s += 64 * sizeof(double);                       // red
+  s += qsp_gemm_smem_bytes(nt);
+  return s + 64;
+}
+
+// Householder QR of S (m x n, column-major, column stride ldS) in place.  On return the
+// leading K = min(m,n) columns of S hold the thin Q and R (K x n, row-major, stride ldR)
+// holds the triangular factor with a non-negative real diagonal.
+__device__ inline void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
+                                          double* red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const int K = imin(m, n);
+  for (int j = 0; j < K; ++j) {
+    cplx* colj = S + (long)j * ldS;
+    // ---- reflector j (warp 0) -------------------------------------------------------
+    if (warp == 0) {
+      double xn2 = 0.0;
+      for (int r = j + 1 + lane; r < m; r += 32) xn2 += cabs2(colj[r]);
+      for (int o = 16; o > 0; o >>= 1) xn2 += shfl_xor_d(xn2, o);
+      const cplx alpha = colj[j];
+      cplx t;
+      double bt;
+      if (xn2 == 0.0 && alpha.y == 0.0) {
+        t = cmake(0.0, 0.0);
+        bt = alpha.x;
+      } else {
+        const double nrm = sqrt(cabs2(alpha) + xn2);
+        bt = alpha.x >= 0.0 ? -nrm : nrm;
+        t = cmake((bt - alpha.x) / bt, -alpha.y / bt);
+        const cplx sc = cdiv(cmake(1.0, 0.0), cmake(alpha.x - bt, alpha.y));
+        for (int r = j + 1 + lane; r < m; r += 32) colj[r] = cmul(colj[r], sc);
+      }
+      if (lane == 0) {
+        tau[j] = t;
+        beta[j] = bt;
+      }
+    }
+    __syncthreads();
+    // ---- apply H_j^H = I - conj(tau) v v^H to the trailing columns ----------------------
+    const cplx tj = tau[j];
+    if (tj.x != 0.0 || tj.y != 0.0) {
+      for (int c = j + 1 + warp; c < n; c += nw) {
+        cplx* colc = S + (long)c * ldS;
+        cplx w = cmake(0.0, 0.0);
+        for (int r = j + lane; r < m; r += 32) {
+          cplx v = (r == j) ? cmake(1.0, 0.0) : colj[r];
+          cfma_conja(w, v, colc[r]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          w.x += shfl_xor_d(w.x, o);
+          w.y += shfl_xor_d(w.y, o);
+        }
+        const cplx f = cmul(cconj(tj), w);
+        for (int r = j + lane; r < m; r += 32) {
+          cplx v = (r == j) ? cmake(1.0, 0.0) : colj[r];
+          colc[r] = csub(colc[r], cmul(f, v));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- R out (upper trapezoid, diagonal = beta), sign-fixed --------------------------
+  for (int idx = tid; idx < K * n; idx += blockDim.x) {
+    const int r = idx / n, c = idx - r * n;
+    cplx v = cmake(0.0, 0.0);
+    if (c == r)
+      v = cmake(beta[r], 0.0);
+    else if (c > r)
+      v = S[(long)c * ldS + r];
+    if (beta[r] < 0.0) v = cmake(-v.x, -v.y);
+    R[(long)r * ldR + c] = v;
+  }
+  __syncthreads();
+  // ---- thin Q in place (zung2r) ---------------------------------------------------------
+  for (int j = K - 1; j >= 0; --j) {
+    cplx* colj = S + (long)j * ldS;
+    const cplx tj = tau[j];
+    if (tj.x != 0.0 || tj.y != 0.0) {
+      for (int c = j + 1 + warp; c < K; c += nw) {
+        cplx* colc = S + (long)c * ldS;
+        cplx w = cmake(0.0, 0.0);
+        for (int r = j + lane; r < m; r += 32) {
+          cplx v = (r == j) ? cmake(1.0, 0.0) : colj[r];
+          cfma_conja(w, v, colc[r]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          w.x += shfl_xor_d(w.x, o);
+          w.y += shfl_xor_d(w.y, o);
+        }
+        const cplx f = cmul(tj, w);
+        for (int r = j + lane; r < m; r += 32) {
+          cplx v = (r == j) ? cmake(1.0, 0.0) : colj[r];
+          colc[r] = csub(colc[r], cmul(f, v));
+        }
+      }
+    }
+    __syncthreads();
+    const double sg = beta[j] < 0.0 ? -1.0 : 1.0;
+    for (int r = tid; r < m; r += blockDim.x) {
+      cplx q;
+      if (r < j)
+        q = cmake(0.0, 0.0);
+      else if (r == j)
+        q = cmake(1.0 - tj.x, -tj.y);
+      else
+        q = cmul(cmake(-tj.x, -tj.y), colj[r]);
+      colj[r] = cscale(q, sg);
+    }
+    __syncthreads();
+  }
+  // columns j+1.. were finished with their own sign before column j touched them only
+  // from the left (H_j), which commutes with the column scaling: nothing left to fix.
+}
+
+__global__ void __launch_bounds__(256) k_left_canon(cplx* __restrict__ mps, int32_t* __restrict__ bonds, int B, int L, int D, int Dm,
+                             int32_t* __restrict__ status) {
+  char* sm = QSP_SMEM_BASE();
+  const int ldS = 2 * Dm + 1;
+  cplx* S = (cplx*)sm;
+  cplx* R = S + (size_t)Dm * ldS;
+  cplx* tau = R + (size_t)Dm * Dm;
+  double* beta = (double*)(tau + Dm);
+  double* red = beta + Dm;
+  cplx* tiles = (cplx*)(((uintptr_t)(red + 64) + 15) & ~(uintptr_t)15);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const long site_stride = (long)D * 2 * D;
+
+  for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    cplx* A = mps + (long)inst * L * site_stride;
+    int32_t* bd = bonds + (long)inst * (L + 1);
+    bool bad = false;
+    for (int i = 0; i <= L; ++i)
+      if (bd[i] > Dm || bd[i] < 1) bad = true;
+    if (bad) {
+      if (tid == 0 && status) status[inst] |= QSP_ST_BOND_OVERFLOW;
+      continue;
+    }
+    int a = bd[0];      // current (new) left bond
+    int a_old = bd[0];  // left extent of the stored tensor = column count of the carried R
+    for (int i = 0; i < L; ++i) {
+      cplx* Ai = A + (long)i * site_stride;
+      const int b = bd[i + 1];
+      const int m = 2 * a, n = b;
+      if (i == 0) {
+        for (int idx = tid; idx < m * n; idx += nt) {
+          const int r = idx / n, c = idx - r * n;
+          S[(long)c * ldS + r] = Ai[(long)r * D + c];
+        }
+        __syncthreads();
+      } else {
+        // S[(k,p), r] = sum_x R[k,x] A[x,p,r]
+        for (int p = 0; p < 2; ++p)
+          cta_zgemm(a, n, a_old, R, Dm, 1, false, Ai + (long)p * D, 2L * D, 1, false, S + p, 2, ldS, false, tiles);
+      }
+      if (i == L - 1) {
+        __syncthreads();
+        for (int idx = tid; idx < m * n; idx += nt) {
+          const int r = idx / n, c = idx - r * n;
+          Ai[(long)r * D + c] = S[(long)c * ldS + r];
+        }
+        __syncthreads();
+        break;
+      }
+      __syncthreads();
+      cta_householder_qr(S, m, n, ldS, R, Dm, tau, beta, red);
+      const int K = imin(m, n);
+      for (int idx = tid; idx < m * K; idx += nt) {
+        const int r = idx / K, c = idx - r * K;
+        Ai[(long)r * D + c] = S[(long)c * ldS + r];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        bd[i] = a;
+        bd[i + 1] = K;
+      }
+      a = K;
+      a_old = n;
+      __syncthreads();
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// right compression (truncating SVD sweep) of a left-canonical MPS
+// ----------------------------------------------------------------------------------
+struct RCompressArgs {
+  const cplx* in;           // [B][L][Din][2][Din]
+  const int32_t* bonds_in;  // [B][L+1]
+  int Din;
+  cplx* out;                // [B][L][Dout][2][Dout]
+  int32_t* bonds_out;       // [B][L+1]
+  int Dout;
+  int B, L;
+  int max_bond;             // 0 = unlimited (up to Dout)
+  double cutoff;            // relative (quimb cutoff_mode='rel'), no renormalisation
+  int normalize;            // divide site 0 by its norm at the end
+  double* svals;            // [B][L-1][nsv] largest singular values per bond (bond i between i-1,i at row i-1), or null
+  int nsv;
+  cplx* amp0;               // [B] <0...0|out> / ||out||  (null to skip)
+  int32_t* status;          // [B]
+  cplx* work;               // per-CTA scratch, rcompress_work_elems() each
+  long work_stride;         // elements per CTA
+  int cap_rows_elems;       // shared elements available for Jacobi rows
+  int tpp;                  // lanes per Jacobi pair
+  int max_sweeps;
+};
+
+// scratch (complex elements per CTA): Mg (Din x 2Dout), Wg (2Dout x (Din+2Dout)),
+// Vg (Dout x 2Dout), Cg (Din x Dout), f (2 x Dout)
+__host__ __device__ inline long rcompress_work_elems(int Din, int Dout) {
+  return (long)Din * 2 * Dout + (long)2 * Dout * (Din + 2 * Dout) + (long)Dout * 2 * Dout + (long)Din * Dout +
+         2L * Dout + 64;
+}
+// shared: Jacobi rows | gemm tiles (aliased onto the same area) + norms/perm + red
+__host__ __device__ inline size_t rcompress_smem_bytes(int jac_elems, int Dout, int nt) {
+  size_t a = (size_t)jac_elems * sizeof(cplx);
+  size_t g = qsp_gemm_smem_bytes(nt);
+  size_t s = a > g ? a : g;
+  s += (size_t)(2 * Dout) * (sizeof(double) + sizeof(int));  // norms + perm
+  s += 64 * sizeof(double);
+  return s + 64;
+}
+
+__global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
+  char* sm = QSP_SMEM_BASE();
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int Din = P.Din, Dout = P.Dout, L = P.L;
+  size_t jac_bytes = (size_t)P.cap_rows_elems * sizeof(cplx);
+  size_t gem_bytes = qsp_gemm_smem_bytes(nt);
+  size_t big = jac_bytes > gem_bytes ? jac_bytes : gem_bytes;
+  cplx* Wsm = (cplx*)sm;
+  cplx* tiles = (cplx*)sm;  // aliased: GEMMs and Jacobi never overlap in time
+  double* norms = (double*)(sm + big);
+  int* perm = (int*)(norms + 2 * Dout);
+  double* red = (double*)(perm + 2 * Dout);
+  red = (double*)(((uintptr_t)red + 7) & ~(uintptr_t)7);
+
+  cplx* Mg = P.work + (long)blockIdx.x * P.work_stride;
+  cplx* Wg = Mg + (long)Din * 2 * Dout;
+  cplx* Vg = Wg + (long)2 * Dout * (Din + 2 * Dout);
+  cplx* Cg = Vg + (long)Dout * 2 * Dout;
+  cplx* fg = Cg + (long)Din * Dout;  // two ping-pong vectors for the <0..0| amplitude
+
+  const long sin = (long)Din * 2 * Din, sout = (long)Dout * 2 * Dout;
+  const int kmax = (P.max_bond > 0) ? imin(P.max_bond, Dout) : Dout;
+
+  for (int inst = blockIdx.x; inst < P.B; inst += gridDim.x) {
+    const cplx* A = P.in + (long)inst * L * sin;
+    const int32_t* bi = P.bonds_in + (long)inst * (L + 1);
+    cplx* O = P.out + (long)inst * L * sout;
+    int32_t* bo = P.bonds_out + (long)inst * (L + 1);
+    int st = 0;
+    bool bad = false;
+    for (int i = 0; i <= L; ++i)
+      if (bi[i] > Din || bi[i] < 1) bad = true;
+    if (bi[L] > Dout || bi[0] > Dout) bad = true;
+    if (bad) {
+      if (tid == 0 && P.status) P.status[inst] |= QSP_ST_BOND_OVERFLOW;
+      continue;
+    }
+    int rp = bi[L];  // r' : current (already truncated) right bond of site i
+    int fcur = 0;
+    if (tid == 0) {
+      bo[L] = bi[L];
+      bo[0] = bi[0];
+    }
+    if (P.amp0)
+      for (int k = tid; k < rp; k += nt) fg[k] = cmake(k == 0 ? 1.0 : 0.0, 0.0);
+    __syncthreads();
+
+    for (int i = L - 1; i >= 0; --i) {
+      const cplx* Ai = A + (long)i * sin;
+      cplx* Oi = O + (long)i * sout;
+      const int b = bi[i], ro = bi[i + 1];  // stored extents of site i
+      const int c = 2 * rp;
+      // ---- M[(x,p),k] = sum_r A[x,p,r] C[r,k]   (C = identity at the last site) -----------
+      if (i == L - 1) {
+        for (int idx = tid; idx < 2 * b * rp; idx += nt) {
+          const int row = idx / rp, k = idx - row * rp;
+          Mg[idx] = Ai[(long)row * Din + k];
+        }
+        __syncthreads();
+      } else {
+        cta_zgemm(2 * b, rp, ro, Ai, Din, 1, false, Cg, Dout, 1, false, Mg, rp, 1, false, tiles);
+      }
+      if (i == 0) {
+        // orthogonality centre: site 0 <- M (b x 2 x rp), optional normalisation
+        double n2 = 0.0;
+        for (int idx = tid; idx < 2 * b * rp; idx += nt) n2 += cabs2(Mg[idx]);
+        n2 = block_sum(n2, red);
+        double sc = 1.0;
+        if (P.normalize) {
+          if (!(n2 > 0.0) || !(n2 < 1e300)) st |= QSP_ST_BADNORM;
+          else sc = 1.0 / sqrt(n2);
+        }
+        for (int idx = tid; idx < 2 * b * rp; idx += nt) {
+          const int row = idx / rp, k = idx - row * rp;
+          Oi[(long)row * Dout + k] = cscale(Mg[idx], sc);
+        }
+        if (P.amp0) {
+          // amplitude <0..0|psi> = sum_k M[(0,0),k] f[k], divided by the norm of psi
+          __syncthreads();
+          if (tid == 0) {
+            cplx acc = cmake(0.0, 0.0);
+            const cplx* f = fg + fcur * Dout;
+            for (int k = 0; k < rp; ++k) cfma(acc, Mg[k], f[k]);
+            const double nn = sqrt(n2);
+            P.amp0[inst] = (nn > 0.0) ? cscale(acc, 1.0 / nn) : cmake(0.0, 0.0);
+          }
+        }
+        __syncthreads();
+        break;
+      }
+      // ---- Jacobi SVD of M (b x c) ----------------------------------------------------
+      const bool modeC = b > c;  // more rows than columns: rotate the columns, accumulate J
+      const int nrows = modeC ? c : b;
+      const int ndot = modeC ? b : c;
+      const int len = modeC ? b + c : c;
+      if (modeC) {
+        // Wg = [ M^T | I ]  (c x (b + c))
+        for (int idx = tid; idx < c * len; idx += nt) {
+          const int r = idx / len, cc = idx - r * len;
+          cplx v;
+          if (cc < b)
+            v = Mg[(long)cc * c + r];
+          else
+            v = cmake((cc - b) == r ? 1.0 : 0.0, 0.0);
+          Wg[idx] = v;
+        }
+      } else {
+        for (int idx = tid; idx < b * c; idx += nt) Wg[idx] = Mg[idx];
+      }
+      __syncthreads();
+      int cap_rows = P.cap_rows_elems / len;
+      if (cap_rows < 2) {
+        st |= QSP_ST_BOND_OVERFLOW;
+        cap_rows = 2;
+      }
+      const double tol = 4e-16 * sqrt((double)ndot);
+      int tpp = P.tpp;
+      while (tpp > 1 && tpp > ndot) tpp >>= 1;
+      if (!jacobi_rows(Wg, nrows, ndot, len, Wsm, cap_rows, tpp, tol * tol, P.max_sweeps, red, (int*)0))
+        st |= QSP_ST_JACOBI_NOCONV;
+      // ---- singular values = row norms; rank them ---------------------------------------
+      {
+        const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+        for (int r = warp; r < nrows; r += nw) {
+          double s2 = 0.0;
+          for (int cc = lane; cc < ndot; cc += 32) s2 += cabs2(Wg[(long)r * len + cc]);
+          for (int o = 16; o > 0; o >>= 1) s2 += shfl_xor_d(s2, o);
+          if (lane == 0) norms[r] = sqrt(s2);
+        }
+      }
+      __syncthreads();
+      for (int r = tid; r < nrows; r += nt) {
+        const double s = norms[r];
+        int rank = 0;
+        for (int q = 0; q < nrows; ++q) {
+          const double t = norms[q];
+          if (t > s || (t == s && q < r)) ++rank;
+        }
+        perm[rank] = r;
+      }
+      __syncthreads();
+      const double smax = norms[perm[0]];
+      int k = 0;
+      for (int q = 0; q < nrows; ++q)
+        if (norms[perm[q]] > P.cutoff * smax) ++k;  // monotone: counts the leading run
+      if (k > kmax) {
+        if (P.max_bond <= 0 || P.max_bond > Dout) st |= QSP_ST_BOND_OVERFLOW;  // cutoff alone did not fit the buffer
+        k = kmax;
+      }
+      k = imax(k, 1);
+      if (P.svals) {
+        double* sv = P.svals + ((long)inst * (L - 1) + (i - 1)) * P.nsv;
+        for (int q = tid; q < P.nsv; q += nt) sv[q] = (q < nrows) ? norms[perm[q]] : 0.0;
+      }
+      // ---- Vh -> out site i (k x 2 x rp) and compact copy Vg (k x c); U s -> Cg (b x k) --
+      if (modeC) {
+        for (int idx = tid; idx < k * c; idx += nt) {
+          const int q = idx / c, cc = idx - q * c;
+          const cplx v = cconj(Wg[(long)perm[q] * len + b + cc]);
+          const int p = cc / rp, kk = cc - p * rp;
+          Oi[((long)q * 2 + p) * Dout + kk] = v;
+          Vg[idx] = v;
+        }
+        for (int idx = tid; idx < b * k; idx += nt) {
+          const int x = idx / k, q = idx - x * k;
+          Cg[(long)x * Dout + q] = Wg[(long)perm[q] * len + x];
+        }
+        __syncthreads();
+      } else {
+        for (int idx = tid; idx < k * c; idx += nt) {
+          const int q = idx / c, cc = idx - q * c;
+          const int r = perm[q];
+          const double s = norms[r];
+          const cplx v = (s > 0.0) ? cscale(Wg[(long)r * len + cc], 1.0 / s) : cmake(0.0, 0.0);
+          const int p = cc / rp, kk = cc - p * rp;
+          Oi[((long)q * 2 + p) * Dout + kk] = v;
+          Vg[idx] = v;
+        }
+        __syncthreads();
+        // U s = M Vh^H
+        cta_zgemm(b, k, c, Mg, c, 1, false, Vg, 1, c, true, Cg, Dout, 1, false, tiles);
+      }
+      // ---- <0...0| amplitude: f_new[q] = sum_kk Vh[q,(0,kk)] f[kk] ---------------------------
+      if (P.amp0) {
+        const cplx* f = fg + fcur * Dout;
+        cplx* fn = fg + (1 - fcur) * Dout;
+        for (int q = tid; q < k; q += nt) {
+          cplx acc = cmake(0.0, 0.0);
+          for (int kk = 0; kk < rp; ++kk) cfma(acc, Vg[(long)q * c + kk], f[kk]);
+          fn[q] = acc;
+        }
+        fcur = 1 - fcur;
+      }
+      if (tid == 0) bo[i] = k;
+      rp = k;
+      __syncthreads();
+    }
+    if (tid == 0 && P.status && st) P.status[inst] |= st;
+    __syncthreads();
+  }
+}

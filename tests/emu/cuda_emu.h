@@ -1,0 +1,155 @@
+// TEST INFRASTRUCTURE: a minimal CUDA-on-CPU emulator (fibers), so that the very same
+// kernel sources under qsp_b200/csrc can be exercised by the CPU test-suite in a
+// container without a GPU.  It is NOT a fallback: the product library (libqsp_b200.so) is
+// built by nvcc only, the python package never loads the emulated build, and only
+// tests/ link against it (tests/emu/build_emu.py -> tests/emu/_build/libqsp_emu.so).
+//
+// Model: every CUDA thread of a block is a ucontext fiber; blocks run one after another.
+// __syncthreads() and the warp shuffles are "group barriers" on which a fiber yields
+// until the whole group has arrived.  Execution is deterministic (fibers run in thread
+// order), so missing barriers usually show up as wrong numbers rather than flakiness.
+#pragma once
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+
+namespace emu {
+struct Fiber {
+  ucontext_t ctx;
+  std::vector<char> stack;
+  bool done = false;
+  unsigned tid = 0;
+};
+struct Group {
+  unsigned count = 0;
+  unsigned gen = 0;
+};
+struct Block {
+  std::vector<Fiber> fibers;
+  ucontext_t sched;
+  std::vector<char> smem;
+  Group bar;
+  std::vector<Group> warp_bar;
+  std::vector<double> xchg;  // 32 doubles per warp
+  std::function<void()> body;
+  unsigned nthreads = 0;
+  int cur = -1;
+};
+extern thread_local Block* g_blk;
+extern thread_local dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+
+inline void yield() { swapcontext(&g_blk->fibers[g_blk->cur].ctx, &g_blk->sched); }
+
+inline void group_sync(Group& g, unsigned size) {
+  unsigned my = g.gen;
+  if (++g.count == size) {
+    g.count = 0;
+    g.gen++;
+  } else {
+    while (g.gen == my) yield();
+  }
+}
+
+inline void trampoline() {
+  Block* b = g_blk;
+  b->body();
+  b->fibers[b->cur].done = true;
+  swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+}
+
+template <class F>
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call) {
+  const unsigned nt = block.x;
+  if (nt % 32 != 0) {
+    fprintf(stderr, "emu: blockDim must be a multiple of 32\n");
+    abort();
+  }
+  for (unsigned bx = 0; bx < grid.x; ++bx) {
+    Block blk;
+    blk.nthreads = nt;
+    blk.smem.assign(smem_bytes + 64, 0);
+    blk.warp_bar.resize(nt / 32);
+    blk.xchg.assign(nt, 0.0);
+    blk.fibers.resize(nt);
+    blk.body = [&]() { kernel_call(); };
+    g_blk = &blk;
+    g_blockIdx = dim3(bx);
+    g_blockDim = block;
+    g_gridDim = grid;
+    for (unsigned t = 0; t < nt; ++t) {
+      Fiber& f = blk.fibers[t];
+      f.tid = t;
+      f.stack.resize(256 * 1024);
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack.data();
+      f.ctx.uc_stack.ss_size = f.stack.size();
+      f.ctx.uc_link = &blk.sched;
+      makecontext(&f.ctx, (void (*)())trampoline, 0);
+    }
+    unsigned alive = nt;
+    while (alive) {
+      for (unsigned t = 0; t < nt; ++t) {
+        Fiber& f = blk.fibers[t];
+        if (f.done) continue;
+        blk.cur = (int)t;
+        g_threadIdx = dim3(t);
+        swapcontext(&blk.sched, &f.ctx);
+        if (f.done) --alive;
+      }
+    }
+    g_blk = nullptr;
+  }
+}
+}  // namespace emu
+
+#define threadIdx (emu::g_threadIdx)
+#define blockIdx (emu::g_blockIdx)
+#define blockDim (emu::g_blockDim)
+#define gridDim (emu::g_gridDim)
+
+inline void __syncthreads() { emu::group_sync(emu::g_blk->bar, emu::g_blk->nthreads); }
+inline void __syncwarp(unsigned = 0xffffffffu) {
+  emu::group_sync(emu::g_blk->warp_bar[emu::g_threadIdx.x / 32], 32);
+}
+inline double __shfl_sync(unsigned, double v, int src, int width = 32) {
+  emu::Block* b = emu::g_blk;
+  unsigned t = emu::g_threadIdx.x, w = t / 32, lane = t % 32;
+  b->xchg[t] = v;
+  emu::group_sync(b->warp_bar[w], 32);
+  unsigned base = lane - (lane % width);
+  double r = b->xchg[w * 32 + base + ((unsigned)src % width)];
+  emu::group_sync(b->warp_bar[w], 32);
+  return r;
+}
+inline double __shfl_xor_sync(unsigned m, double v, int mask, int width = 32) {
+  unsigned lane = emu::g_threadIdx.x % 32;
+  return __shfl_sync(m, v, (int)((lane ^ (unsigned)mask) % (unsigned)width), width);
+}
+inline int __shfl_sync(unsigned m, int v, int src, int width = 32) {
+  return (int)__shfl_sync(m, (double)v, src, width);
+}
+inline int __shfl_xor_sync(unsigned m, int v, int mask, int width = 32) {
+  return (int)__shfl_xor_sync(m, (double)v, mask, width);
+}
+inline char* emu_dynamic_smem() {
+  uintptr_t p = (uintptr_t)emu::g_blk->smem.data();
+  return (char*)((p + 15) & ~(uintptr_t)15);
+}
