@@ -267,6 +267,29 @@ extern "C" int qsp_overlap(const qsp_c128* a, const int32_t* bonds_a, int D_a, c
   return check_launch();
 }
 
+// FP64 throughput probe (bench.py measures the DFMA roofline with it; MEASURED_PEAKS.json
+// carries no FP64 figure).  16 independent FMA chains per thread.
+__global__ void k_dfma_probe(double* out, int iters) {
+  double a[16];
+  const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-9 * blockIdx.x;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = k * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = fma(a[k], x, y);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == 12345.678) out[0] = s;  // never true; keeps the loop alive
+}
+extern "C" int qsp_dfma_probe(double* out, int blocks, int threads, int iters, void* stream) {
+  if (!out || blocks <= 0 || threads <= 0 || threads % 32) return QSP_ERR_ARG;
+  QSP_LAUNCH(k_dfma_probe, blocks, threads, 0, (qsp_stream_t)stream, out, iters);
+  ++g_launches;
+  return check_launch();
+}
+
 // ------------------------------------------------------------------------------------
 // input pipeline: MPSPreparation.__init__ + sequential.py:38-40
 // ------------------------------------------------------------------------------------

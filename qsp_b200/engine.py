@@ -1,0 +1,183 @@
+"""Batched host driver: torch only owns device memory and streams, every tensor operation
+is a call into libqsp_b200.so (include/qsp_b200.h).
+
+Layout: a batch of B MPS of L sites is `mps[B, L, D, 2, D]` complex128 with the
+live bond extents in `bonds[B, L+1]` int32; element (l, p, r) of a site is mps[b, i, l, p, r].
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _runtime
+from ._capi import FLAG_NO_ENCODED, FLAG_SECOND_PASS, QspError
+
+CUTOFF = 1e-10  # quimb's default relative cutoff used throughout the reference path
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def pack_mps_list(mps_list, D=None):
+    """list of MPS (each a list of (l,2,r) numpy arrays) -> (mps[B,L,D,2,D], bonds[B,L+1]) numpy."""
+    B, L = len(mps_list), len(mps_list[0])
+    if D is None:
+        D = max(max(a.shape[0], a.shape[2]) for m in mps_list for a in m)
+    arr = np.zeros((B, L, D, 2, D), np.complex128)
+    bonds = np.ones((B, L + 1), np.int32)
+    for b, m in enumerate(mps_list):
+        if len(m) != L:
+            raise ValueError("all MPS of a batch must have the same length")
+        bonds[b, 0] = m[0].shape[0]
+        for i, a in enumerate(m):
+            arr[b, i, : a.shape[0], :, : a.shape[2]] = a
+            bonds[b, i + 1] = a.shape[2]
+    return arr, bonds
+
+
+def unpack_mps(arr, bonds):
+    arr = arr.cpu().numpy() if isinstance(arr, torch.Tensor) else np.asarray(arr)
+    bonds = bonds.cpu().numpy() if isinstance(bonds, torch.Tensor) else np.asarray(bonds)
+    return [[arr[b, i, : bonds[b, i], :, : bonds[b, i + 1]].copy() for i in range(arr.shape[1])]
+            for b in range(arr.shape[0])]
+
+
+def working_bond(max_in, L, layers, max_bond):
+    """Padded bond D the layer loop needs (include/qsp_b200.h, qsp_seq_prepare)."""
+    if max_bond and max_bond > 0:
+        return int(max(max_in, max_bond))
+    cap = 2 ** (L // 2)
+    return int(max(max_in, min(max_in * 2 ** layers, cap)))
+
+
+class SeqResult:
+    """Device-resident results of one batched layer loop (layer-major)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class Engine:
+    """Owns the workspace for one (B_chunk, L, D, layers, max_bond, flags) shape."""
+
+    def __init__(self, device="cuda:0"):
+        self.lib = _runtime.lib()
+        self.device = torch.device(device)
+        self._work = None
+        self._work_key = None
+
+    # ---- memory ---------------------------------------------------------------------------
+    def _workspace(self, nbytes):
+        if self._work is None or self._work.numel() < nbytes:
+            self._work = None
+            self._work = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._work
+
+    def seq_workspace_bytes(self, B, L, D, layers, max_bond, flags):
+        n = self.lib.qsp_seq_prepare_workspace_bytes(B, L, D, layers, max_bond, flags)
+        if n == 0:
+            raise QspError(
+                f"shape not supported by this build's shared-memory kernels: L={L} D={D} layers={layers} "
+                f"max_bond={max_bond} (QSP_ERR_UNSUPPORTED)")
+        return n
+
+    def pick_chunk(self, B, L, D, layers, max_bond, flags, budget_bytes=None):
+        """Largest chunk of instances whose workspace fits the memory budget."""
+        if budget_bytes is None:
+            free, _ = torch.cuda.mem_get_info(self.device)
+            budget_bytes = int(free * 0.6)
+        c = B
+        while c > 1 and self.seq_workspace_bytes(c, L, D, layers, max_bond, flags) > budget_bytes:
+            c = (c + 1) // 2
+        return c
+
+    # ---- input pipeline ---------------------------------------------------------------------
+    def prepare_target(self, mps, bonds, cutoff=CUTOFF):
+        """MPSPreparation.__init__ (tsp.py:63-77) + sequential.py:38-40, in place on device."""
+        B, L, D = mps.shape[0], mps.shape[1], mps.shape[2]
+        status = torch.zeros(B, dtype=torch.int32, device=self.device)
+        nb = self.lib.qsp_prepare_target_workspace_bytes(B, L, D)
+        if nb == 0:
+            raise QspError(f"bond dimension {D} not supported by this build (QSP_ERR_UNSUPPORTED)")
+        work = self._workspace(nb)
+        self.lib.qsp_prepare_target(_p(mps), _p(bonds), B, L, D, cutoff, _p(status), _p(work), nb,
+                                    _runtime.current_stream_ptr())
+        return status
+
+    # ---- the layer loop ---------------------------------------------------------------------
+    def seq_prepare(self, target, bonds, layers, max_bond=0, cutoff=CUTOFF, overlaps_gap=4, second_pass=False,
+                    encoded=True, want_final=False, chunk=None):
+        """sequential_unitary_circuit (sequential.py:42-85) for target[B,L,D,2,D] (device)."""
+        if target.dtype != torch.complex128 or bonds.dtype != torch.int32:
+            raise TypeError("target must be complex128 and bonds int32")
+        if not (target.is_cuda and target.is_contiguous() and bonds.is_contiguous()):
+            raise ValueError("target/bonds must be contiguous CUDA tensors")
+        B, L, D = target.shape[0], target.shape[1], target.shape[2]
+        flags = (FLAG_SECOND_PASS if second_pass else 0) | (0 if encoded else FLAG_NO_ENCODED)
+        dev = self.device
+        ov = torch.empty((layers, B), dtype=torch.complex128, device=dev)
+        dis = torch.empty((layers, B), dtype=torch.complex128, device=dev)
+        G = torch.empty((layers, B, L, 4, 4), dtype=torch.complex128, device=dev)
+        kind = torch.empty((layers, B, L), dtype=torch.int32, device=dev)
+        sv = torch.empty((layers, B, max(L - 1, 1), 2), dtype=torch.float64, device=dev)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        fin = torch.empty_like(target) if want_final else None
+        finb = torch.empty_like(bonds) if want_final else None
+        if chunk is None:
+            chunk = self.pick_chunk(B, L, D, layers, max_bond, flags)
+        stream = _runtime.current_stream_ptr()
+        for b0 in range(0, B, chunk):
+            b1 = min(B, b0 + chunk)
+            n = b1 - b0
+            nb = self.seq_workspace_bytes(n, L, D, layers, max_bond, flags)
+            work = self._workspace(nb)
+            whole = n == B
+            c_ov = ov if whole else torch.empty((layers, n), dtype=torch.complex128, device=dev)
+            c_dis = dis if whole else torch.empty((layers, n), dtype=torch.complex128, device=dev)
+            c_G = G if whole else torch.empty((layers, n, L, 4, 4), dtype=torch.complex128, device=dev)
+            c_kind = kind if whole else torch.empty((layers, n, L), dtype=torch.int32, device=dev)
+            c_sv = sv if whole else torch.empty((layers, n, max(L - 1, 1), 2), dtype=torch.float64, device=dev)
+            self.lib.qsp_seq_prepare(_p(target[b0:b1]), _p(bonds[b0:b1]), n, L, D, layers, max_bond, cutoff,
+                                     overlaps_gap, flags, _p(c_ov), _p(c_dis), _p(c_G), _p(c_kind), _p(c_sv),
+                                     _p(fin[b0:b1]) if want_final else None,
+                                     _p(finb[b0:b1]) if want_final else None, _p(status[b0:b1]), _p(work), nb, stream)
+            if not whole:
+                ov[:, b0:b1] = c_ov
+                dis[:, b0:b1] = c_dis
+                G[:, b0:b1] = c_G
+                kind[:, b0:b1] = c_kind
+                sv[:, b0:b1] = c_sv
+        return SeqResult(overlaps=ov, dis_overlaps=dis, G=G, kind=kind, d2_svals=sv, status=status, final_mps=fin,
+                         final_bonds=finb, layers=layers, overlaps_gap=overlaps_gap)
+
+    # ---- encoded state (apply_unitary_layers_on_wfn + overlap), used by the facade's self-check
+    def encoded_overlap(self, G, kind, target, bonds, cutoff=CUTOFF):
+        """<target| U_0 ... U_{n-1} |0..0> for G[n,B,L,4,4], kind[n,B,L] (core.py:217-221 +
+        right_canonize(normalize) + norm_mps_ovrlap, tsp.py:130-132)."""
+        n, B, L = G.shape[0], G.shape[1], G.shape[2]
+        D = target.shape[2]
+        De = 2 ** min(n, L // 2)
+        dev = self.device
+        enc = torch.zeros((B, L, De, 2, De), dtype=torch.complex128, device=dev)
+        enc[:, :, 0, 0, 0] = 1.0
+        encb = torch.ones((B, L + 1), dtype=torch.int32, device=dev)
+        enc2 = torch.empty((B, L, 2 * De, 2, 2 * De), dtype=torch.complex128, device=dev)
+        enc2b = torch.empty((B, L + 1), dtype=torch.int32, device=dev)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        nb = max(self.lib.qsp_right_compress_workspace_bytes(B, L, 2 * De, De),
+                 self.lib.qsp_overlap_workspace_bytes(B, L, De, D))
+        if nb == 0:
+            raise QspError("encoded state too large for this build (QSP_ERR_UNSUPPORTED)")
+        work = self._workspace(nb)
+        s = _runtime.current_stream_ptr()
+        for k in range(n - 1, -1, -1):
+            Gk, kk = G[k].contiguous(), kind[k].contiguous()
+            self.lib.qsp_apply_forward_layer(_p(enc), _p(encb), De, _p(Gk), _p(kk), _p(enc2), _p(enc2b), 2 * De, B, L,
+                                             _p(status), s)
+            self.lib.qsp_left_canonize(_p(enc2), _p(enc2b), B, L, 2 * De, _p(status), s)
+            self.lib.qsp_right_compress(_p(enc2), _p(enc2b), 2 * De, _p(enc), _p(encb), De, B, L, 0, cutoff,
+                                        1 if k == 0 else 0, None, 0, None, _p(status), _p(work), nb, s)
+        res = torch.empty(B, dtype=torch.complex128, device=dev)
+        self.lib.qsp_overlap(_p(enc), _p(encb), De, _p(target), _p(bonds), D, B, L, _p(res), _p(work), nb, s)
+        return res, status

@@ -1,0 +1,103 @@
+"""Circuit emission (qsp/q_circs/qiskit_circuit.py:34-70).  The circuit object is
+assembled in Python, as in the reference.  With qiskit installed the reference's own
+construction is used (circ.unitary + transpile to {cx, u3}); without it a plain gate list
+with the same ordering / endianness and the accessors the facade reads (tsp.py:146) stands
+in.  The L <= 16 statevector cross-check (qiskit_circuit.py:52-67) runs on the GPU."""
+import numpy as np
+
+try:  # pragma: no cover - qiskit is not in the build image
+    import qiskit
+except Exception:  # noqa: BLE001
+    qiskit = None
+
+
+class GateListCircuit:
+    """Stand-in for qiskit.QuantumCircuit: gates in application order, qiskit's qubit-list
+    convention (first listed qubit = least significant index of the matrix)."""
+
+    def __init__(self, num_qubits):
+        self.num_qubits = num_qubits
+        self.gates = []  # (matrix, [qubits])
+
+    def unitary(self, u, qubits):
+        self.gates.append((np.asarray(u, dtype=np.complex128), list(qubits)))
+
+    def size(self):
+        return len(self.gates)
+
+    def num_nonlocal_gates(self):
+        return sum(1 for _, q in self.gates if len(q) > 1)
+
+    def count_ops(self):
+        return {"unitary2": self.num_nonlocal_gates(), "unitary1": self.size() - self.num_nonlocal_gates()}
+
+    def depth(self):
+        busy = [0] * self.num_qubits
+        for _, q in self.gates:
+            d = max(busy[i] for i in q) + 1
+            for i in q:
+                busy[i] = d
+        return max(busy) if busy else 0
+
+    def cx_u3_upper_bound(self):
+        """Gate counts after a {cx, u3} transpile are bounded by 3 cx + 8 u3 per two-qubit
+        unitary and 1 u3 per one-qubit unitary (KAK); the exact qiskit numbers need qiskit."""
+        n2 = self.num_nonlocal_gates()
+        n1 = self.size() - n2
+        return {"size": 11 * n2 + n1, "num_nonlocal_gates": 3 * n2}
+
+    def statevector(self, device="cuda:0"):
+        """|psi> = circuit |0..0>, returned with axis i = qubit i (torch tensor on `device`)."""
+        import torch
+
+        L = self.num_qubits
+        psi = torch.zeros((2,) * L, dtype=torch.complex128, device=device)
+        psi[(0,) * L] = 1.0
+        for u, q in self.gates:
+            g = torch.from_numpy(u).to(device)
+            if len(q) == 1:
+                psi = torch.movedim(torch.tensordot(g, psi, dims=([1], [q[0]])), 0, q[0])
+            else:
+                hi, lo = q[1], q[0]  # matrix index = 2*bit(q[1]) + bit(q[0])
+                g4 = g.reshape(2, 2, 2, 2)
+                psi = torch.movedim(torch.tensordot(g4, psi, dims=([2, 3], [hi, lo])), (0, 1), (hi, lo))
+        return psi
+
+
+def _dense_from_mps(arrays, device):
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(arrays[0])).to(device).to(torch.complex128)
+    for a in arrays[1:]:
+        t = torch.tensordot(t, torch.from_numpy(np.ascontiguousarray(a)).to(device).to(torch.complex128), dims=([t.dim() - 1], [0]))
+    return t.reshape(t.shape[1:-1])
+
+
+def circuit_from_unitary_layers(unitary_layers, L, target_mps=None, device="cuda:0"):
+    """qiskit_circuit.py:34-70: layers in reverse order, sites ascending, a 4x4 G on qubits
+    [it+1, it], a 2x2 G on [it]; for L <= 16 the statevector overlap with the dense target."""
+    use_qiskit = qiskit is not None
+    circ = qiskit.QuantumCircuit(L) if use_qiskit else GateListCircuit(L)
+    shadow = GateListCircuit(L)
+    for it_layer in reversed(range(len(unitary_layers))):
+        for seg in unitary_layers[it_layer]:
+            start, end, Gs = seg[0], seg[1], seg[2]
+            for it in range(start, end + 1):
+                u = Gs[it - start].data
+                qubits = [it] if it == end else [it + 1, it]
+                circ.unitary(u, qubits)
+                if use_qiskit:
+                    shadow.unitary(u, qubits)
+    if use_qiskit:  # pragma: no cover
+        circ = qiskit.transpile(circ, basis_gates=["cx", "u3"])
+    else:
+        shadow = circ
+    overlap_from_seq_circ = None
+    arrays = getattr(target_mps, "arrays", None)
+    if L <= 16 and arrays is not None:
+        import torch
+
+        vec = shadow.statevector(device)
+        orig = _dense_from_mps(arrays, device)
+        overlap_from_seq_circ = float(torch.abs(torch.sum(torch.conj(orig) * vec)).item())
+    return circ, overlap_from_seq_circ

@@ -1,0 +1,122 @@
+"""Drop-in facade for qsp/tsp.py:36-149 -- MPSPreparation(tensor_array, shape=...) and
+.sequential_unitary_circuit(...) -> (overlap, circ) -- plus a batched variant that keeps
+many independent MPS on the device (the reference loops over instances in Python,
+examples/benchmarks.py:49-61)."""
+import numpy as np
+import torch
+
+from .engine import Engine, pack_mps_list, unpack_mps, working_bond
+from .mps import MPSState, gates_to_gs_lst, to_lpr
+from .sequential import sequential_unitary_circuit
+from .tsp_helper_routines import cl_zero_mps  # noqa: F401  (re-exported like the reference module)
+
+
+def _arrays_from_input(tensor_array, shape):
+    if isinstance(tensor_array, MPSState):
+        return [a.copy() for a in tensor_array.arrays]
+    if hasattr(tensor_array, "arrays") and hasattr(tensor_array, "permute_arrays"):  # a quimb MPS
+        q = tensor_array.copy()
+        q.permute_arrays("lpr")
+        return to_lpr(list(q.arrays), "lpr")
+    return to_lpr(tensor_array, shape)
+
+
+class MPSPreparation:
+    """tsp.py:36-77.  data: list of numpy arrays (three-index, two-index at the ends) in
+    `shape` order, or an MPSState / quimb MatrixProductState."""
+
+    def __init__(self, tensor_array, shape="lrp", device="cuda:0"):
+        self._engine = Engine(device)
+        arrays = _arrays_from_input(tensor_array, shape)
+        D = max(max(a.shape[0], a.shape[2]) for a in arrays)
+        a, b = pack_mps_list([arrays], D)
+        a, b = torch.from_numpy(a).to(self._engine.device), torch.from_numpy(b).to(self._engine.device)
+        # normalize(); normalize(); compress('right')  (tsp.py:68-72)
+        st = self._engine.prepare_target(a, b)
+        if int(st.max().item()):
+            raise RuntimeError(f"target preparation failed with device status {int(st.max().item()):#x}")
+        target_mps = MPSState(unpack_mps(a, b)[0])
+        target_mps._prepared = True
+        self.phys_dim = target_mps.phys_dim()
+        self.target_mps = target_mps
+        self.shape = shape
+        self.L = target_mps.L
+
+    def sequential_unitary_circuit(self, num_seq_layers, do_compression=False, max_bond_dim=None, verbose=False):
+        """tsp.py:79-149: returns (overlap, circ)."""
+        if self.phys_dim != 2:
+            raise ValueError("only supports mps with physical dimesnion=2")
+        if do_compression is True and max_bond_dim is None:
+            raise ValueError("since do_compression is True, max_bond_dim>0 should be specified")
+        print(f"preparing mps using sequential unitaries (num_seq_layers={num_seq_layers})...")
+        data = sequential_unitary_circuit(self.target_mps, num_seq_layers, do_compression=do_compression,
+                                          max_bond_dim=max_bond_dim, verbose=verbose, engine=self._engine)
+        self.shape = "lpr"  # sequential.py:38 permutes the arrays in place
+        self.seq_data = data
+        unitaries, circ = data["unitaries"], data["circ"]
+
+        # sanity check (tsp.py:129-135): rebuild the encoded state from the unitaries and re-measure
+        overlap = self._encoded_overlap(unitaries)
+        assert np.abs(overlap - data["overlaps"][-1]) < 1e-12, "overlap from seqential unitary construction does not match!"
+
+        overlap_from_seq_circ = data["overlap_from_seq_circ"]
+        temp_str = "" if overlap_from_seq_circ is None else f" (from circ {overlap_from_seq_circ:0.8f})"
+        print(f"overlap from static seq. preparation = {np.abs(overlap):0.8f}{temp_str},\n"
+              f"n_gates={circ.size()}, n_2qg={circ.num_nonlocal_gates()}\n")
+        return overlap, circ
+
+    def _encoded_overlap(self, unitaries):
+        from .mps import gs_lst_to_gates
+
+        eng, L = self._engine, self.L
+        Gk = [gs_lst_to_gates(u, L) for u in unitaries]
+        G = torch.from_numpy(np.stack([g for g, _ in Gk])[:, None]).to(eng.device)
+        kind = torch.from_numpy(np.stack([k for _, k in Gk])[:, None]).to(eng.device)
+        D = self.target_mps.max_bond()
+        a, b = pack_mps_list([self.target_mps.arrays], D)
+        a, b = torch.from_numpy(a).to(eng.device), torch.from_numpy(b).to(eng.device)
+        res, st = eng.encoded_overlap(G, kind, a, b)
+        return complex(res[0].item())
+
+
+class BatchedMPSPreparation:
+    """Many independent targets of equal length, resident on one GPU (SURVEY.md section 8e:
+    instances are the only parallel axis of this path)."""
+
+    def __init__(self, mps_list=None, shape="lrp", device="cuda:0", packed=None, prepared=False):
+        self.engine = Engine(device)
+        if packed is not None:
+            self.mps, self.bonds = packed
+        else:
+            arrs = [_arrays_from_input(m, shape) for m in mps_list]
+            a, b = pack_mps_list(arrs)
+            self.mps = torch.from_numpy(a).to(self.engine.device)
+            self.bonds = torch.from_numpy(b).to(self.engine.device)
+        self.B, self.L = self.mps.shape[0], self.mps.shape[1]
+        if not prepared:
+            self.status = self.engine.prepare_target(self.mps, self.bonds)
+        self.seq_data = None
+
+    def sequential_unitary_circuit(self, num_seq_layers, do_compression=False, max_bond_dim=None, overlaps_gap=4,
+                                   second_pass=False, chunk=None):
+        """Returns (overlaps[B] complex128 tensor on the device, SeqResult)."""
+        if do_compression is True and max_bond_dim is None:
+            raise ValueError("since do_compression is True, max_bond_dim>0 should be specified")
+        mb = int(max_bond_dim) if do_compression else 0
+        D_in = self.mps.shape[2]
+        D = working_bond(int(self.bonds.max().item()), self.L, num_seq_layers, mb)
+        tgt = self.mps
+        if D != D_in:
+            tgt = torch.zeros((self.B, self.L, D, 2, D), dtype=torch.complex128, device=self.engine.device)
+            m = min(D, D_in)
+            tgt[:, :, :m, :, :m] = self.mps[:, :, :m, :, :m]
+        res = self.engine.seq_prepare(tgt, self.bonds, num_seq_layers, max_bond=mb, overlaps_gap=overlaps_gap,
+                                      second_pass=second_pass, chunk=chunk)
+        self.seq_data = res
+        return res.overlaps[num_seq_layers - 1], res
+
+    def unitaries(self, b):
+        """Reference-style list of Gs_lst layers for instance b."""
+        G = self.seq_data.G[:, b].cpu().numpy()
+        kind = self.seq_data.kind[:, b].cpu().numpy()
+        return [gates_to_gs_lst(G[k], kind[k]) for k in range(G.shape[0])]

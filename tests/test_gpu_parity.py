@@ -1,0 +1,272 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the
+same seeded inputs and against the golden fixtures taken from the reference's pickles.
+Tolerances: overlaps 1e-10 absolute, singular values 1e-12 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import gates_to_layers, pack_batch, unpack_batch
+from oracle import qsp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def drv():
+    import torch
+
+    assert torch.cuda.is_available(), "run with -m gpu on a CUDA box"
+    from helpers import CudaDriver
+
+    d = CudaDriver()
+    assert d.lib.is_device_build()
+    return d
+
+
+def _prepared(mps):
+    t = O.prepare_target(mps, "lpr")
+    O.right_canonize(t, normalize=True)
+    return t
+
+
+def _load_gold(tag):
+    z = np.load(os.path.join(GOLD, f"{tag}.npz"))
+    b, m = z["bonds"], z["mps"]
+    return z, [m[i, : b[i], :, : b[i + 1]].copy() for i in range(len(b) - 1)]
+
+
+def _dev(drv, mps_list, D=None):
+    a, b = pack_batch(mps_list, D)
+    return drv.from_host(a), drv.from_host(b)
+
+
+# ---------------------------------------------------------------------------------------
+# unit level
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L,chi", [(6, 4), (12, 16), (20, 64), (9, 5)])
+def test_left_canonize_matches_oracle(drv, L, chi):
+    mpss = [O.random_mps(L, chi, 10 + s) for s in range(3)]
+    for m in mpss:  # keep entries O(1)
+        for i in range(L):
+            m[i] = m[i] / np.linalg.norm(m[i])
+    a, b = _dev(drv, mpss, chi)
+    st = drv.left_canonize(a, b)
+    assert drv.to_host(st).max() == 0
+    got = unpack_batch(drv.to_host(a), drv.to_host(b))
+    for m, g in zip(mpss, got):
+        ref = O.left_canonize(O.copy_mps(m))
+        assert O.bonds_of(ref) == O.bonds_of(g)
+        for x, y in zip(ref, g):
+            assert np.abs(x - y).max() < 1e-12
+
+
+@pytest.mark.parametrize("L,chi,max_bond", [(8, 8, 4), (12, 16, 0), (16, 64, 32), (10, 32, 2), (30, 128, 64)])
+def test_right_compress_matches_oracle(drv, L, chi, max_bond):
+    """state, bond profile and singular values of the truncating sweep (quimb right_compress)."""
+    mpss = []
+    for s in range(2):
+        m = O.random_mps(L, chi, 20 + s)
+        nrm = np.sqrt(O.inner(m, m).real)
+        m[0] = m[0] / nrm
+        mpss.append(O.left_canonize(m))
+    Dout = max_bond if max_bond else chi
+    a, b = _dev(drv, mpss, chi)
+    out, bo, st, sv, amp = drv.right_compress(a, b, Dout, max_bond=max_bond, normalize=1, nsv=4, amp0=True)
+    assert drv.to_host(st).max() == 0
+    got = unpack_batch(drv.to_host(out), drv.to_host(bo))
+    sv, amp = drv.to_host(sv), drv.to_host(amp)
+    for k, (m, g) in enumerate(zip(mpss, got)):
+        svl = []
+        ref = O.right_compress(O.copy_mps(m), max_bond=max_bond or None, svals=svl)  # literal quimb steps
+        O.right_canonize(ref, normalize=True)
+        assert O.bonds_of(ref) == O.bonds_of(g)
+        assert abs(abs(O.inner(g, ref)) - 1.0) < 1e-12
+        assert abs(O.inner(g, g).real - 1.0) < 1e-12
+        for j, s in enumerate(svl):  # bond L-1 first
+            i = L - 1 - j
+            n = min(4, len(s))
+            assert np.allclose(sv[k, i - 1, :n], s[:n], rtol=1e-12, atol=1e-14 * s[0])
+        assert abs(amp[k] - O.norm_mps_ovrlap(ref, O.cl_zero_mps(L)) * np.exp(1j * np.angle(O.inner(g, ref)))) < 1e-12
+        # right-canonical output
+        for i in range(1, L):
+            x = g[i].reshape(g[i].shape[0], -1)
+            assert np.abs(x @ x.conj().T - np.eye(x.shape[0])).max() < 1e-12
+
+
+def test_unitaries_match_oracle_canonical(drv):
+    tg = [_prepared(O.random_mps(10, 8, 30 + s)) for s in range(4)]
+    d2s = [O.d2_truncate(t) for t in tg]
+    a, b = _dev(drv, d2s, 2)
+    G, kind, st = drv.generate_unitaries(a, b)
+    assert drv.to_host(st).max() == 0
+    G, kind = drv.to_host(G), drv.to_host(kind)
+    for k, d2 in enumerate(d2s):
+        ref = O.generate_unitaries(d2, completion="canonical")
+        got = gates_to_layers(G[k], kind[k])
+        assert [(s, e) for s, e, _ in ref] == [(s, e) for s, e, _ in got]
+        for (_, _, gr), (_, _, gg) in zip(ref, got):
+            for x, y in zip(gr, gg):
+                assert np.abs(x - y).max() < 1e-12
+        O.unitaries_sanity_check(got)
+
+
+def test_apply_layers_match_oracle(drv):
+    """inverse layer on a left-canonical MPS and forward layer on a right-canonical one give
+    the same STATES as the reference's gate_split staircases (core.py:126-141, 224-240)."""
+    L, chi = 10, 8
+    tg = [_prepared(O.random_mps(L, chi, 40 + s)) for s in range(2)]
+    layers = [O.generate_bond_d_unitary(t, completion="canonical") for t in tg]
+    from helpers import layers_to_gates
+
+    Gk = [layers_to_gates(l, L) for l in layers]
+    G = drv.from_host(np.stack([g for g, _ in Gk]))
+    kind = drv.from_host(np.stack([k for _, k in Gk]))
+    lc = [O.left_canonize(O.copy_mps(t)) for t in tg]
+    a, b = _dev(drv, lc, chi)
+    out, bo, st = drv.apply_layer(a, b, G, kind, 2 * chi, inverse=True)
+    assert drv.to_host(st).max() == 0
+    got = unpack_batch(drv.to_host(out), drv.to_host(bo))
+    for t, l, g in zip(tg, layers, got):
+        ref = O.apply_inverse_unitary_layer_on_wfn(l, t)
+        assert abs(O.inner(g, ref) - 1.0) < 1e-12 and abs(O.inner(g, g) - 1.0) < 1e-12
+    a, b = _dev(drv, tg, chi)
+    out, bo, st = drv.apply_layer(a, b, G, kind, 2 * chi, inverse=False)
+    got = unpack_batch(drv.to_host(out), drv.to_host(bo))
+    for t, l, g in zip(tg, layers, got):
+        ref = O.apply_unitary_layer_on_wfn(l, t)
+        assert abs(O.inner(g, ref) - 1.0) < 1e-12
+
+
+def test_overlap_matches_oracle(drv):
+    L = 14
+    xs = [O.random_mps(L, 6, 50 + s) for s in range(3)]
+    ys = [O.random_mps(L, 16, 60 + s) for s in range(3)]
+    a, ba = _dev(drv, xs, 6)
+    b, bb = _dev(drv, ys, 16)
+    res = drv.to_host(drv.overlap(a, ba, b, bb))
+    for k in range(3):
+        ref = O.inner(xs[k], ys[k])
+        assert abs(res[k] - ref) < 1e-12 * abs(ref) + 1e-300
+
+
+# ---------------------------------------------------------------------------------------
+# the layer loop
+# ---------------------------------------------------------------------------------------
+def _check_pipeline(drv, tgts, layers, max_bond, D, tol=1e-10, same_convention=True, flags=0):
+    a, b = _dev(drv, tgts, D)
+    r = drv.seq_prepare(a, b, layers, max_bond=max_bond, flags=flags)
+    r = {k: drv.to_host(v) for k, v in r.items()}
+    assert r["status"].max() == 0, r["status"]
+    ev = [i for i in range(layers) if i % 4 == 0 or i == layers - 1]
+    for k, tgt in enumerate(tgts):
+        dev_layers = [gates_to_layers(r["G"][j, k], r["kind"][j, k]) for j in range(layers)]
+        for lay in dev_layers:
+            O.unitaries_sanity_check(lay)
+        kw = dict(do_compression=max_bond > 0, max_bond_dim=max_bond or None)
+        # teacher-forced: the device's unitaries through the literal reference steps
+        tf = O.sequential_unitary_circuit(tgt, layers, unitaries_override=dev_layers, record_svals=True, **kw)
+        assert np.abs(np.array(tf["disentangled_mps_overlaps"]) - r["dis"][:, k]).max() < tol
+        assert np.abs(np.array(tf["overlaps"]) - r["overlaps"][ev, k]).max() < tol
+        # per-bond singular values of every layer's D=2 truncation, 1e-12 relative
+        for j in range(layers):
+            for q, s in enumerate(tf["d2_svals"][j]):
+                i = len(tgt) - 1 - q
+                n = min(2, len(s))
+                assert np.allclose(r["d2_svals"][j, k, i - 1, :n], s[:n], rtol=1e-11, atol=1e-13 * s[0])
+        if same_convention:
+            sc = O.sequential_unitary_circuit(tgt, layers, completion="canonical", **kw)
+            assert np.abs(np.array(sc["disentangled_mps_overlaps"]) - r["dis"][:, k]).max() < tol
+            assert np.abs(np.array(sc["overlaps"]) - r["overlaps"][ev, k]).max() < tol
+    return r
+
+
+def test_pipeline_readme_config(drv):
+    """BASELINE configs[0]: README example L=10 chi=4, 4 layers, no compression."""
+    tg = [_prepared(O.to_lpr(O.readme_mps(10, 4, s), "lrp")) for s in range(3)]
+    _check_pipeline(drv, tg, 4, 0, 32)
+
+
+@pytest.mark.parametrize("L,chi,layers", [(12, 8, 3), (24, 16, 4), (16, 32, 2)])
+def test_pipeline_random_compressed(drv, L, chi, layers):
+    tg = [_prepared(O.random_mps(L, chi, 70 + s)) for s in range(3)]
+    _check_pipeline(drv, tg, layers, chi, chi)
+
+
+def test_pipeline_second_pass_flag(drv):
+    """the reference's trailing cutoff-only compress() (sequential.py:56-57) changes nothing at 1e-10."""
+    tg = [_prepared(O.random_mps(14, 8, 80 + s)) for s in range(2)]
+    r1 = _check_pipeline(drv, tg, 3, 8, 8)
+    r2 = _check_pipeline(drv, tg, 3, 8, 8, flags=1)
+    assert np.abs(r1["dis"] - r2["dis"]).max() < 1e-12
+
+
+def test_pipeline_chi64(drv):
+    """headline bond dimension on a short chain (the oracle needs seconds per instance)."""
+    tg = [_prepared(O.random_mps(16, 64, 90 + s)) for s in range(2)]
+    _check_pipeline(drv, tg, 2, 64, 64)
+
+
+def test_golden_heisenberg_layer1(drv):
+    """reference pickle examples/data/heisenberg_L32_dist0.8000.pkl: layer-1 overlap
+    0.5704604532578025 (gauge invariant), depths/gate_counts [32, ...]."""
+    z, mps = _load_gold("heisenberg_L32")
+    tg = _prepared(mps)
+    a, b = _dev(drv, [tg], 32)
+    r = drv.seq_prepare(a, b, 1, max_bond=0)
+    r = {k: drv.to_host(v) for k, v in r.items()}
+    assert r["status"].max() == 0
+    assert abs(abs(r["overlaps"][0, 0]) - 0.5704604532578025) < 1e-11
+    assert abs(abs(r["dis"][0, 0]) - abs(z["overlaps"][0])) < 1e-11
+    lay = gates_to_layers(r["G"][0, 0], r["kind"][0, 0])
+    assert O.unitaries_specs(lay) == (int(z["depths"][0]), int(z["gate_counts"][0]))
+
+
+def test_golden_p4_layer1_and_teacher_forced(drv):
+    """reference pickle examples/data/P4_6-31G_dist2.0000.pkl: layer-1 overlap
+    0.9670549179903772; deeper layers teacher-forced (degenerate Schmidt pairs make the
+    same-convention comparison ill-conditioned for this state)."""
+    z, mps = _load_gold("P4_L16")
+    tg = _prepared(mps)
+    a, b = _dev(drv, [tg], 45)
+    r = drv.seq_prepare(a, b, 1, max_bond=0)
+    r = {k: drv.to_host(v) for k, v in r.items()}
+    assert abs(abs(r["overlaps"][0, 0]) - 0.9670549179903772) < 1e-11
+    _check_pipeline(drv, [tg], 3, 45, 45, same_convention=False)
+
+
+def test_facade_readme_example(drv, capsys):
+    """README.md:24-36 through the drop-in facade, statevector fidelity of the emitted circuit."""
+    from qsp_b200.tsp import MPSPreparation
+
+    arr = O.readme_mps(10, 4, 7)
+    prep = MPSPreparation(arr, shape="lrp")
+    overlap, circ = prep.sequential_unitary_circuit(num_seq_layers=4)
+    ref_ov, ref = O.mps_preparation_sequential(arr, 4, completion="canonical")
+    assert abs(overlap - ref_ov) < 1e-10
+    d = prep.seq_data
+    assert set(d) >= {"disentangled_mps_overlaps", "overlaps", "it_Ds", "depths", "gate_counts", "energies",
+                      "unitaries", "circ", "overlap_from_seq_circ"}
+    assert d["it_Ds"] == [0, 3] and d["depths"] == ref["depths"] and d["gate_counts"] == ref["gate_counts"]
+    # emitted-circuit statevector fidelity equals the MPS overlap (qiskit_circuit.py:52-67)
+    assert abs(d["overlap_from_seq_circ"] - abs(overlap)) < 1e-10
+    layers = [[[s, e, [g.data for g in gs]] for s, e, gs, _, _ in lay] for lay in d["unitaries"]]
+    psi = O.circuit_statevector(layers, 10)
+    dense = O.mps_to_dense(ref["mps_orig"])
+    assert abs(abs(np.vdot(dense, psi)) - abs(overlap)) < 1e-10
+    assert circ.size() == sum(ref["gate_counts"][-1:]) and circ.num_nonlocal_gates() > 0
+    out = capsys.readouterr().out
+    assert "preparing mps using sequential unitaries (num_seq_layers=4)" in out
+
+
+def test_facade_errors(drv):
+    from qsp_b200.tsp import MPSPreparation
+
+    prep = MPSPreparation(O.readme_mps(6, 2, 1), shape="lrp")
+    with pytest.raises(ValueError):
+        prep.sequential_unitary_circuit(2, do_compression=True)
+    prep.phys_dim = 3
+    with pytest.raises(ValueError):
+        prep.sequential_unitary_circuit(2)
