@@ -1,0 +1,196 @@
+"""Kernel LOGIC on the CPU: the very sources under qsp_b200/csrc compiled against the fiber
+emulator (tests/emu/cuda_emu.h) and driven through the same C ABI, compared with the oracle
+on small seeded cases.  (The GPU parity tests in test_gpu_parity.py are the ones that
+count for parity; these catch indexing / ordering bugs where no GPU is available.)"""
+import numpy as np
+import pytest
+
+import proto_fused as P
+from helpers import HostDriver, gates_to_layers, layers_to_gates, pack_batch, unpack_batch
+from oracle import qsp_oracle as O
+
+
+@pytest.fixture(scope="module")
+def drv():
+    d = HostDriver()
+    assert not d.lib.is_device_build()
+    return d
+
+
+def _prepared(mps):
+    t = O.prepare_target(mps, "lpr")
+    O.right_canonize(t, normalize=True)
+    return t
+
+
+def test_left_canonize(drv):
+    mpss = [O.random_mps(7, 5, s) for s in range(2)]
+    for m in mpss:
+        for i in range(7):
+            m[i] = m[i] / np.linalg.norm(m[i])
+    a, b = pack_batch(mpss, 6)
+    assert drv.left_canonize(a, b).max() == 0
+    for m, g in zip(mpss, unpack_batch(a, b)):
+        ref = O.left_canonize(O.copy_mps(m))
+        assert O.bonds_of(ref) == O.bonds_of(g)
+        assert max(np.abs(x - y).max() for x, y in zip(ref, g)) < 1e-13
+
+
+@pytest.mark.parametrize("max_bond", [0, 3, 2])
+def test_right_compress(drv, max_bond):
+    mpss = []
+    for s in range(2):
+        m = O.random_mps(7, 6, 10 + s)
+        m[0] = m[0] / np.sqrt(O.inner(m, m).real)
+        mpss.append(O.left_canonize(m))
+    a, b = pack_batch(mpss, 6)
+    out, bo, st, sv, amp = drv.right_compress(a, b, 6, max_bond=max_bond, normalize=1, nsv=3, amp0=True)
+    assert st.max() == 0
+    for k, (m, g) in enumerate(zip(mpss, unpack_batch(out, bo))):
+        svl = []
+        ref = O.right_compress(O.copy_mps(m), max_bond=max_bond or None, svals=svl)
+        O.right_canonize(ref, normalize=True)
+        assert O.bonds_of(ref) == O.bonds_of(g)
+        assert abs(O.inner(g, ref) - 1.0) < 1e-13
+        for j, s in enumerate(svl):
+            n = min(3, len(s))
+            assert np.allclose(sv[k, 7 - 1 - j - 1, :n], s[:n], rtol=1e-12)
+        assert abs(amp[k] - O.norm_mps_ovrlap(ref, O.cl_zero_mps(7))) < 1e-13
+
+
+def test_block_jacobi_path(drv):
+    """more rows than fit the (emulated) shared buffer are rotated block-pair by block-pair:
+    force it by shrinking the row capacity through a tall matrix (b > capacity)."""
+    # L=2 chain: site 1 is (b, 2, 1) -> mode C (b > c); site rows live in mode R for the bulk case below
+    m = O.random_mps(8, 16, 77)
+    m[0] = m[0] / np.sqrt(O.inner(m, m).real)
+    m = O.left_canonize(m)
+    a, b = pack_batch([m], 16)
+    out, bo, st, sv, _ = drv.right_compress(a, b, 16, max_bond=8, normalize=1, nsv=2)
+    assert st.max() == 0
+    ref = O.right_compress(O.copy_mps(m), max_bond=8)
+    O.right_canonize(ref, normalize=True)
+    g = unpack_batch(out, bo)[0]
+    assert abs(O.inner(g, ref) - 1.0) < 1e-12
+
+
+def test_unitaries_and_layers(drv):
+    L = 8
+    tg = [_prepared(O.random_mps(L, 4, 20 + s)) for s in range(2)]
+    d2s = [O.d2_truncate(t) for t in tg]
+    a, b = pack_batch(d2s, 2)
+    G, kind, st = drv.generate_unitaries(a, b)
+    assert st.max() == 0
+    for k, d2 in enumerate(d2s):
+        ref = O.generate_unitaries(d2, completion="canonical")
+        got = gates_to_layers(G[k], kind[k])
+        for (s0, e0, gr), (s1, e1, gg) in zip(ref, got):
+            assert (s0, e0) == (s1, e1)
+            assert max(np.abs(x - y).max() for x, y in zip(gr, gg)) < 1e-13
+    lc = [O.left_canonize(O.copy_mps(t)) for t in tg]
+    a, b = pack_batch(lc, 4)
+    out, bo, st = drv.apply_layer(a, b, G, kind, 8, inverse=True)
+    assert st.max() == 0
+    for t, k, g in zip(tg, range(2), unpack_batch(out, bo)):
+        ref = O.apply_inverse_unitary_layer_on_wfn(gates_to_layers(G[k], kind[k]), t)
+        assert abs(O.inner(g, ref) - 1.0) < 1e-13
+    a, b = pack_batch(tg, 4)
+    out, bo, st = drv.apply_layer(a, b, G, kind, 8, inverse=False)
+    for t, k, g in zip(tg, range(2), unpack_batch(out, bo)):
+        ref = O.apply_unitary_layer_on_wfn(gates_to_layers(G[k], kind[k]), t)
+        assert abs(O.inner(g, ref) - 1.0) < 1e-13
+
+
+def test_segmented_layer(drv):
+    """a D=2 state with collapsed bonds: one-site segments, one-qubit segment ends (H5)."""
+    L = 7
+    one = np.zeros((1, 2, 1), complex)
+    one[0, :, 0] = [0.6, 0.8j]
+    bell = np.zeros((1, 2, 2), complex)
+    bell[0, 0, 0], bell[0, 1, 1] = 0.8, 0.6
+    mid = np.zeros((2, 2, 2), complex)
+    mid[0, 0, 0], mid[0, 1, 1], mid[1, 1, 0], mid[1, 0, 1] = 0.6, 0.8, 0.8, -0.6
+    end = np.zeros((2, 2, 1), complex)
+    end[0, 0, 0] = end[1, 1, 0] = 1
+    d2 = [one.copy(), bell.copy(), mid.copy(), end.copy(), one.copy(), bell.copy(), end.copy()]
+    O.right_canonize(d2, normalize=True)
+    a, b = pack_batch([d2], 2)
+    G, kind, st = drv.generate_unitaries(a, b)
+    assert st.max() == 0 and kind[0].tolist() == [1, 2, 2, 1, 1, 2, 1]
+    ref = O.generate_unitaries(d2, completion="canonical")
+    got = gates_to_layers(G[0], kind[0])
+    assert [(s, e) for s, e, _ in got] == [(s, e) for s, e, _ in ref] == [(0, 0), (1, 3), (4, 4), (5, 6)]
+    for (_, _, gr), (_, _, gg) in zip(ref, got):
+        assert max(np.abs(x - y).max() for x, y in zip(gr, gg)) < 1e-13
+    # apply to a chi=4 state: inverse on left-canonical, forward on right-canonical
+    psi = _prepared(O.random_mps(L, 4, 5))
+    a, b = pack_batch([O.left_canonize(O.copy_mps(psi))], 4)
+    out, bo, st = drv.apply_layer(a, b, G, kind, 8, inverse=True)
+    assert st.max() == 0
+    g = unpack_batch(out, bo)[0]
+    assert abs(O.inner(g, O.apply_inverse_unitary_layer_on_wfn(ref, psi)) - 1.0) < 1e-13
+    a, b = pack_batch([psi], 4)
+    out, bo, st = drv.apply_layer(a, b, G, kind, 8, inverse=False)
+    g = unpack_batch(out, bo)[0]
+    assert abs(O.inner(g, O.apply_unitary_layer_on_wfn(ref, psi)) - 1.0) < 1e-13
+
+
+def test_overlap(drv):
+    xs = [O.random_mps(6, 3, 1), O.random_mps(6, 3, 2)]
+    ys = [O.random_mps(6, 5, 3), O.random_mps(6, 5, 4)]
+    a, ba = pack_batch(xs, 3)
+    b, bb = pack_batch(ys, 5)
+    res = drv.overlap(a, ba, b, bb)
+    for k in range(2):
+        ref = O.inner(xs[k], ys[k])
+        assert abs(res[k] - ref) < 1e-13 * abs(ref)
+
+
+def test_prepare_target(drv):
+    raw = [O.to_lpr(O.readme_mps(6, 3, s), "lrp") for s in range(2)]
+    a, b = pack_batch(raw, 4)
+    assert drv.prepare_target(a, b).max() == 0
+    for r, g in zip(raw, unpack_batch(a, b)):
+        ref = O.prepare_target(r, "lpr")
+        O.right_canonize(ref, normalize=True)
+        assert O.bonds_of(ref) == O.bonds_of(g)
+        assert abs(O.inner(g, ref) - 1.0) < 1e-13
+
+
+@pytest.mark.parametrize("case", ["compressed", "readme_nocomp", "second_pass"])
+def test_layer_loop(drv, case):
+    if case == "readme_nocomp":
+        tg = [_prepared(O.to_lpr(O.readme_mps(6, 2, s), "lrp")) for s in range(2)]
+        layers, mb, D, flags = 3, 0, 8, 0
+    else:
+        tg = [_prepared(O.random_mps(6, 4, 30 + s)) for s in range(2)]
+        layers, mb, D, flags = 2, 4, 4, (1 if case == "second_pass" else 0)
+    a, b = pack_batch(tg, D)
+    r = drv.seq_prepare(a, b, layers, max_bond=mb, flags=flags)
+    assert r["status"].max() == 0
+    ev = [i for i in range(layers) if i % 4 == 0 or i == layers - 1]
+    for k, t in enumerate(tg):
+        kw = dict(do_compression=mb > 0, max_bond_dim=mb or None)
+        sc = O.sequential_unitary_circuit(t, layers, completion="canonical", record_svals=True, **kw)
+        assert np.abs(np.array(sc["disentangled_mps_overlaps"]) - r["dis"][:, k]).max() < 1e-12
+        assert np.abs(np.array(sc["overlaps"]) - r["overlaps"][ev, k]).max() < 1e-12
+        dev_layers = [gates_to_layers(r["G"][j, k], r["kind"][j, k]) for j in range(layers)]
+        tf = O.sequential_unitary_circuit(t, layers, unitaries_override=dev_layers, **kw)
+        assert np.abs(np.array(tf["disentangled_mps_overlaps"]) - r["dis"][:, k]).max() < 1e-12
+        for j in range(layers):
+            for q, s in enumerate(sc["d2_svals"][j]):
+                n = min(2, len(s))
+                assert np.allclose(r["d2_svals"][j, k, len(t) - 1 - q - 1, :n], s[:n], rtol=1e-11)
+        fin = unpack_batch(r["final"], r["final_bonds"])[k]
+        assert abs(O.inner(fin, sc["final_mps"]) - 1.0) < 1e-11
+
+
+def test_status_bits_and_error_codes(drv):
+    # bond larger than the padded buffer allows -> QSP_ST_BOND_OVERFLOW, instance skipped
+    tg = [_prepared(O.to_lpr(O.readme_mps(8, 4, 0), "lrp"))]
+    a, b = pack_batch(tg, 4)
+    r = drv.seq_prepare(a, b, 2, max_bond=0)  # no compression: bonds want to double beyond D=4
+    assert r["status"][0] & 2
+    # unsupported size is reported before anything is launched
+    assert drv.lib.qsp_seq_prepare_workspace_bytes(1, 10, 512, 2, 512, 0) == 0
+    assert drv.lib._qsp_left_canonize(None, None, 1, 4, 4, None, None) == 1
