@@ -157,3 +157,151 @@ __device__ inline bool jacobi_rows(cplx* Wg, int nrows, int ndot, int len, cplx*
   if (sweeps_out) *sweeps_out = sweeps;
   return conv;
 }
+
+// ----------------------------------------------------------------------------------
+// Register-resident odd-even Jacobi (the fast path).
+//
+// Rows are laid out on a line; rounds alternate between the pairs (2t, 2t+1) and
+// (2t+1, 2t+2) and the two rows of a pair swap places after every visit, so n rounds
+// visit each of the n(n-1)/2 pairs exactly once (odd-even transposition ordering).
+// Team t keeps the row at the odd position 2t+1 in REGISTERS for the whole SVD; the rows at
+// even positions live in shared memory.  A visit therefore costs two shared reads and one
+// shared write of a row instead of four reads + two writes, and a 128 x 128 complex128
+// matrix (256 KB) stays on chip: 128 KB in registers, 128 KB in shared memory.
+// Lane tl of a team owns columns tl, tl+tpp, ... (CPL of them at most).
+// ----------------------------------------------------------------------------------
+template <int CPL>
+__device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int ndot, int len, cplx* S, int tpp, double tol2,
+                                      int max_sweeps, double* red, int* sweeps_out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int team = tid / tpp, tl = tid % tpp;
+  const int ne = (nrows + 1) >> 1, no = nrows >> 1;
+  cplx R[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = tl + j * tpp;
+    R[j] = (team < no && c < len) ? Wg[(long)(2 * team + 1) * len + c] : cmake(0.0, 0.0);
+  }
+  for (int idx = tid; idx < ne * len; idx += nt) {
+    const int r = idx / len, c = idx - r * len;
+    S[idx] = Wg[(long)(2 * r) * len + c];
+  }
+  __syncthreads();
+  bool conv = false;
+  int sweeps = 0;
+  while (sweeps < max_sweeps) {
+    int nrot = 0;
+    for (int r = 0; r < nrows; ++r) {
+      const int slot = team + (r & 1);
+      const bool valid = (team < no) && (slot < ne);
+      cplx* xs = S + (long)slot * len;
+      double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int c = tl + j * tpp;
+          if (c < ndot) {
+            const cplx x = xs[c], y = R[j];
+            al = fma(x.x, x.x, al);
+            al = fma(x.y, x.y, al);
+            be = fma(y.x, y.x, be);
+            be = fma(y.y, y.y, be);
+            gx = fma(x.x, y.x, gx);
+            gx = fma(x.y, y.y, gx);
+            gy = fma(x.y, y.x, gy);
+            gy = fma(-x.x, y.y, gy);
+          }
+        }
+      }
+      for (int o = tpp >> 1; o > 0; o >>= 1) {
+        al += shfl_xor_d(al, o);
+        be += shfl_xor_d(be, o);
+        gx += shfl_xor_d(gx, o);
+        gy += shfl_xor_d(gy, o);
+      }
+      if (valid) {
+        const double g2 = gx * gx + gy * gy;
+        const double ab = al * be;
+        if (ab > 1e-280 && g2 > tol2 * ab) {
+          const double ag = sqrt(g2);
+          const double zeta = (be - al) / (2.0 * ag);
+          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double cs = 1.0 / sqrt(1.0 + t * t);
+          const double sn = cs * t;
+          const double sx = sn * gx / ag, sy = sn * gy / ag;  // s e^{i phi}
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const int c = tl + j * tpp;
+            if (c < len) {
+              const cplx x = xs[c], y = R[j];
+              cplx xn, yn;
+              xn.x = cs * x.x - (sx * y.x - sy * y.y);
+              xn.y = cs * x.y - (sx * y.y + sy * y.x);
+              yn.x = cs * y.x + (sx * x.x + sy * x.y);
+              yn.y = cs * y.y + (sx * x.y - sy * x.x);
+              xs[c] = yn;  // the rows trade places
+              R[j] = xn;
+            }
+          }
+          if (tl == 0) ++nrot;
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const int c = tl + j * tpp;
+            if (c < len) {
+              const cplx x = xs[c];
+              xs[c] = R[j];
+              R[j] = x;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    ++sweeps;
+    if ((int)(block_sum((double)nrot, red) + 0.5) == 0) {
+      conv = true;
+      break;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int c = tl + j * tpp;
+    if (team < no && c < len) Wg[(long)(2 * team + 1) * len + c] = R[j];
+  }
+  for (int idx = tid; idx < ne * len; idx += nt) {
+    const int r = idx / len, c = idx - r * len;
+    Wg[(long)(2 * r) * len + c] = S[idx];
+  }
+  __syncthreads();
+  if (sweeps_out) *sweeps_out = sweeps;
+  return conv;
+}
+
+// Dispatcher: the register-resident path when the matrix fits (rows <= 2 teams, <= 16
+// columns per lane, even rows fit the shared buffer), else the generic shared/L2 path.
+__device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndot, int len, cplx* Wsm, int cap_elems, int tpp_hint,
+                                       double tol2, int max_sweeps, double* red, int* sweeps_out) {
+  if (nrows <= 1) {
+    if (sweeps_out) *sweeps_out = 0;
+    return true;
+  }
+  const int nt = blockDim.x;
+  const int need_teams = nrows >> 1;
+  int tpp = 32;
+  while (tpp > 1 && nt / tpp < need_teams) tpp >>= 1;
+  const int cpl = (len + tpp - 1) / tpp;
+  const long need_elems = (long)((nrows + 1) >> 1) * len;
+  if (nt / tpp >= need_teams && cpl <= 16 && need_elems <= cap_elems) {
+    if (cpl <= 2) return jacobi_rows_oe<2>(Wg, nrows, ndot, len, Wsm, tpp, tol2, max_sweeps, red, sweeps_out);
+    if (cpl <= 4) return jacobi_rows_oe<4>(Wg, nrows, ndot, len, Wsm, tpp, tol2, max_sweeps, red, sweeps_out);
+    if (cpl <= 8) return jacobi_rows_oe<8>(Wg, nrows, ndot, len, Wsm, tpp, tol2, max_sweeps, red, sweeps_out);
+    return jacobi_rows_oe<16>(Wg, nrows, ndot, len, Wsm, tpp, tol2, max_sweeps, red, sweeps_out);
+  }
+  int cap_rows = cap_elems / len;
+  if (cap_rows < 2) cap_rows = 2;
+  int t2 = tpp_hint;
+  while (t2 > 1 && t2 > ndot) t2 >>= 1;
+  return jacobi_rows(Wg, nrows, ndot, len, Wsm, cap_rows, t2, tol2, max_sweeps, red, sweeps_out);
+}

@@ -363,15 +363,9 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         for (int idx = tid; idx < b * c; idx += nt) Wg[idx] = Mg[idx];
       }
       __syncthreads();
-      int cap_rows = P.cap_rows_elems / len;
-      if (cap_rows < 2) {
-        st |= QSP_ST_BOND_OVERFLOW;
-        cap_rows = 2;
-      }
+      if (P.cap_rows_elems / len < 2) st |= QSP_ST_BOND_OVERFLOW;
       const double tol = 4e-16 * sqrt((double)ndot);
-      int tpp = P.tpp;
-      while (tpp > 1 && tpp > ndot) tpp >>= 1;
-      if (!jacobi_rows(Wg, nrows, ndot, len, Wsm, cap_rows, tpp, tol * tol, P.max_sweeps, red, (int*)0))
+      if (!jacobi_svd_rows(Wg, nrows, ndot, len, Wsm, P.cap_rows_elems, P.tpp, tol * tol, P.max_sweeps, red, (int*)0))
         st |= QSP_ST_JACOBI_NOCONV;
       // ---- singular values = row norms; rank them ---------------------------------------
       {

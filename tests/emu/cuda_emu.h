@@ -28,6 +28,7 @@ struct dim3 {
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 
