@@ -27,6 +27,12 @@ import numpy as np  # noqa: E402
 from qsp_b200 import flop_model  # noqa: E402
 
 METRIC = "sequential_prep_mps_per_sec"
+_T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
 UNIT = "MPS/s"
 
 
@@ -53,30 +59,18 @@ def workload_name(a):
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle (numpy restatement of the reference path; quimb is not installable)
 # --------------------------------------------------------------------------------------
-def _cpu_one(args):
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    os.environ["OMP_NUM_THREADS"] = "1"
-    L, chi, layers, seed = args
-    from oracle import qsp_oracle as O
-
-    t = O.prepare_target(O.random_mps(L, chi, seed), "lpr")
-    t0 = time.time()
-    O.sequential_unitary_circuit(t, layers, do_compression=True, max_bond_dim=chi, completion="lapack")
-    return time.time() - t0
-
-
-def cpu_sample(L, chi, layers_sample, n_inst, cores):
-    """n_inst instances x layers_sample layers on `cores` single-threaded workers -> wall seconds."""
-    import multiprocessing as mp
-
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    os.environ["OMP_NUM_THREADS"] = "1"
-    ctx = mp.get_context("fork")
-    jobs = [(L, chi, layers_sample, 1234 + i) for i in range(n_inst)]
-    with ctx.Pool(cores) as pool:
-        t0 = time.time()
-        pool.map(_cpu_one, jobs)
-        return time.time() - t0
+def cpu_sample(L, chi, layers_sample, n_inst, cores, reps=1, timeout=420):
+    """n_inst instances x layers_sample layers on `cores` single-threaded oracle workers, in a
+    separate interpreter (BLAS threads pinned to 1 through the environment) -> list of wall seconds."""
+    env = dict(os.environ)
+    for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        env[k] = "1"
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_bench_worker.py"), str(L), str(chi), str(layers_sample),
+                          str(n_inst), str(cores), str(reps)], env=env, capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError(out.stderr[-2000:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
 
 
 def cpu_cores():
@@ -84,14 +78,18 @@ def cpu_cores():
         n = len(os.sched_getaffinity(0))
     except Exception:  # noqa: BLE001
         n = os.cpu_count() or 1
-    return max(1, min(n, 32))
+    return max(1, min(n, 16))
 
 
 def cpu_baseline(a):
     """Bounded sample: one layer of the workload on `cores` instances (one per worker),
     extrapolated linearly to `layers` layers (with compression on every layer costs the same)."""
     cores = cpu_cores()
-    wall = cpu_sample(a.L, a.chi, 1, cores, cores)
+    log(f"cpu_baseline: {cores} oracle workers, 1 layer each ...")
+    try:
+        wall = cpu_sample(a.L, a.chi, 1, cores, cores)[0]
+    except Exception as e:  # noqa: BLE001
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {str(e)[:200]}"}
     v = cores / (wall * a.layers)
     return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{cores} instances x 1 of {a.layers} layers of {workload_name(a)} "
@@ -104,17 +102,16 @@ def run_reference(a):
     if rank != 0:
         return
     cores = cpu_cores()
-    for _ in range(min(a.warmup, 1)):
-        cpu_sample(a.L, a.chi, 1, cores, cores)
-    walls = [cpu_sample(a.L, a.chi, 1, cores, cores) for _ in range(a.steps)]
+    steps = max(1, min(a.steps, 3))
+    walls = cpu_sample(a.L, a.chi, 1, cores, cores, reps=steps, timeout=900)
     t = float(np.mean(walls))
     v = cores / (t * a.layers)
     sample = (f"each step = {cores} instances x 1 of {a.layers} layers of {workload_name(a)} on {cores} "
               f"single-threaded workers (numpy/scipy restatement; quimb, the reference's engine, cannot be installed); "
               f"MPS/s = instances / (wall x {a.layers})")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": min(a.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
         "config": {"workload": workload_name(a), "L": a.L, "chi": a.chi, "layers": a.layers},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -232,9 +229,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log(f"inputs ready: B={B} L={L} chi={chi} layers={layers} world={world}")
     for _ in range(a.warmup):
         res = step()
     barrier()
+    log("warm-up done")
     assert int(res.status.max().item()) == 0, f"device status {res.status.unique().tolist()}"
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = lib.launch_count()
@@ -246,6 +245,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    log(f"timed region done: {ms / a.steps:.1f} ms/step")
     launches = lib.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -301,9 +301,12 @@ def main():
             dist.destroy_process_group()
         return
 
+    log(f"e2e done: {e2e}")
     # ---- roofline of the dominant kernel (k_right_compress, 2chi -> chi), timed live --------
     roof = kernel_roofline(torch, eng, lib, tgt, tb, a, dev)
+    log(f"kernel roofline done: {roof['kernel_ms']:.1f} ms, frac {roof['frac']}")
     cpu = None if a.no_cpu_baseline else cpu_baseline(a)
+    log("cpu baseline done")
     fm = flop_model.flops_per_mps(L, chi, layers)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -126,6 +126,11 @@ int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bonds, int B, 
                     qsp_c128* dis_overlaps, qsp_c128* G, int32_t* kind, double* d2_svals, qsp_c128* final_mps,
                     int32_t* final_bonds, int32_t* status, void* work, size_t work_bytes, void* stream);
 
+/* Measurement aid: when set (device pointer to >= 8*grid int64, zeroed by the caller), every
+ * qsp_right_compress launch adds per-CTA clock64 cycles: [0] A*C GEMM, [1] staging, [2] Jacobi,
+ * [3] ranking, [4] Vh/U s, [5] Jacobi sweeps, [6] sites.  NULL (default) disables it. */
+void qsp_set_profile_buffer(void* buf);
+
 /* Measurement aid: blocks x threads threads each run `iters` rounds of 16 independent
  * double-precision FMAs (flops = blocks*threads*iters*32).  bench.py times it to obtain the
  * FP64 roofline denominator, which MEASURED_PEAKS.json does not carry. */

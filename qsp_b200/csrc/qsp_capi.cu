@@ -16,6 +16,7 @@ thread_local dim3 emu::g_threadIdx, emu::g_blockIdx, emu::g_blockDim, emu::g_gri
 #endif
 
 static long long g_launches = 0;
+static long long* g_prof = nullptr;  // optional device buffer [grid][8] for k_right_compress phase cycles
 static char g_err[256] = "";
 
 // ------------------------------------------------------------------------------------
@@ -112,10 +113,12 @@ static bool plan_rcompress(int Din, int Dout, const DevInfo& d, RCompressPlan* p
   int tpp = 32;
   while (tpp > 2 && p->nt / tpp < imin(Dout, Din)) tpp >>= 1;  // >= one team per pair when possible
   p->tpp = tpp;
-  // largest Jacobi working set: mode R (b <= c): 2Dout x 2Dout; mode C (c < b): c x (b + c)
-  long needR = 4L * Dout * Dout;
+  // largest Jacobi working set (rows padded to the team width, <= 32 columns of zeros):
+  // mode R (b <= c): 2Dout x 2Dout; mode C (c < b): c x (b + c)
+  auto r32 = [](long x) { return (x + 31) / 32 * 32; };
+  long needR = 2L * Dout * r32(2L * Dout);
   long cmax = imin(2 * Dout, Din - 1);
-  long needC = cmax > 0 ? cmax * ((long)Din + cmax) : 0;
+  long needC = cmax > 0 ? cmax * (r32(Din) + r32(cmax)) : 0;
   long need = needR > needC ? needR : needC;
   size_t fixed = rcompress_smem_bytes(0, Dout, p->nt) - qsp_gemm_smem_bytes(p->nt);
   long budget = ((long)d.max_smem - (long)fixed) / (long)sizeof(cplx);
@@ -123,7 +126,7 @@ static bool plan_rcompress(int Din, int Dout, const DevInfo& d, RCompressPlan* p
   if (budget < gem) return false;
   long je = need < budget ? need : budget;
   // at least two rows of the longest possible row must fit
-  long maxlen = imax(2 * Dout, Din + (int)cmax);
+  long maxlen = imax((int)r32(2 * Dout), (int)(r32(Din) + r32(cmax)));
   if (je < 2 * maxlen) return false;
   p->jac_elems = (int)je;
   p->smem = rcompress_smem_bytes(p->jac_elems, Dout, p->nt);
@@ -142,6 +145,7 @@ extern "C" int qsp_is_device_build(void) {
 #endif
 }
 extern "C" const char* qsp_last_cuda_error(void) { return g_err; }
+extern "C" void qsp_set_profile_buffer(void* p) { g_prof = (long long*)p; }
 extern "C" long long qsp_launch_count(void) { return g_launches; }
 
 extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* stream) {
@@ -206,6 +210,7 @@ extern "C" int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, i
   a.cap_rows_elems = p.jac_elems;
   a.tpp = p.tpp;
   a.max_sweeps = 60;
+  a.prof = g_prof;
   QSP_LAUNCH(k_right_compress, grid, p.nt, p.smem, (qsp_stream_t)stream, a);
   ++g_launches;
   return check_launch();

@@ -21,6 +21,14 @@ typedef cudaStream_t qsp_stream_t;
 
 #include <stdint.h>
 
+#ifdef QSP_EMU
+inline long long qsp_clock() { return 0; }
+inline double qsp_rsqrt(double x) { return 1.0 / sqrt(x); }
+#else
+__device__ __forceinline__ long long qsp_clock() { return clock64(); }
+__device__ __forceinline__ double qsp_rsqrt(double x) { return rsqrt(x); }
+#endif
+
 #define QSP_FULL_MASK 0xffffffffu
 
 struct __attribute__((aligned(16))) cplx {

@@ -168,23 +168,46 @@ __device__ inline bool jacobi_rows(cplx* Wg, int nrows, int ndot, int len, cplx*
 // even positions live in shared memory.  A visit therefore costs two shared reads and one
 // shared write of a row instead of four reads + two writes, and a 128 x 128 complex128
 // matrix (256 KB) stays on chip: 128 KB in registers, 128 KB in shared memory.
-// Lane tl of a team owns columns tl, tl+tpp, ... (CPL of them at most).
+// Lane tl of a team owns columns tl, tl+tpp, ... ; rows are zero-padded to a multiple of
+// tpp columns (ldw = jlen*tpp) and the Gram part to jdot*tpp columns, so the column loops
+// are branch-free and warp-uniform.
 // ----------------------------------------------------------------------------------
+__host__ __device__ inline int jacobi_oe_tpp(int nt, int nrows) {
+  int tpp = 32;
+  while (tpp > 1 && nt / tpp < (nrows >> 1)) tpp >>= 1;
+  return tpp;
+}
+
+// rotation parameters from the Gram entries: x' = cs x - se y, y' = conj(se) x + cs y
+// with se = s e^{i phi}.  One sqrt, one reciprocal, one rsqrt (no division by |g|).
+__device__ __forceinline__ void jacobi_rotation(double al, double be, double gx, double gy, double g2, double& cs,
+                                                double& sx, double& sy) {
+  const double d = be - al;
+  const double h = sqrt(fma(d, d, 4.0 * g2));
+  const double w = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);  // t e^{i phi} = w g
+  const double t2 = w * w * g2;
+  cs = qsp_rsqrt(1.0 + t2);
+  const double cw = cs * w;
+  sx = cw * gx;
+  sy = cw * gy;
+}
+
 template <int CPL>
-__device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int ndot, int len, cplx* S, int tpp, double tol2,
-                                      int max_sweeps, double* red, int* sweeps_out) {
+__device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int jlen, int s_off, int tpp, double tol2,
+                                            int max_sweeps, int red_off, int* sweeps_out) {
+  cplx* S = (cplx*)(QSP_SMEM_BASE() + s_off);
+  double* red = (double*)(QSP_SMEM_BASE() + red_off);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int team = tid / tpp, tl = tid % tpp;
+  const int ldw = jlen * tpp;
   const int ne = (nrows + 1) >> 1, no = nrows >> 1;
   cplx R[CPL];
 #pragma unroll
-  for (int j = 0; j < CPL; ++j) {
-    const int c = tl + j * tpp;
-    R[j] = (team < no && c < len) ? Wg[(long)(2 * team + 1) * len + c] : cmake(0.0, 0.0);
-  }
-  for (int idx = tid; idx < ne * len; idx += nt) {
-    const int r = idx / len, c = idx - r * len;
-    S[idx] = Wg[(long)(2 * r) * len + c];
+  for (int j = 0; j < CPL; ++j)
+    R[j] = (team < no && j < jlen) ? Wg[(long)(2 * team + 1) * ldw + tl + j * tpp] : cmake(0.0, 0.0);
+  for (int idx = tid; idx < ne * ldw; idx += nt) {
+    const int r = idx / ldw, c = idx - r * ldw;
+    S[idx] = Wg[(long)(2 * r) * ldw + c];
   }
   __syncthreads();
   bool conv = false;
@@ -194,23 +217,20 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int ndot, int l
     for (int r = 0; r < nrows; ++r) {
       const int slot = team + (r & 1);
       const bool valid = (team < no) && (slot < ne);
-      cplx* xs = S + (long)slot * len;
+      cplx* xs = S + (long)(valid ? slot : 0) * ldw + tl;
       double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
-      if (valid) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          const int c = tl + j * tpp;
-          if (c < ndot) {
-            const cplx x = xs[c], y = R[j];
-            al = fma(x.x, x.x, al);
-            al = fma(x.y, x.y, al);
-            be = fma(y.x, y.x, be);
-            be = fma(y.y, y.y, be);
-            gx = fma(x.x, y.x, gx);
-            gx = fma(x.y, y.y, gx);
-            gy = fma(x.y, y.x, gy);
-            gy = fma(-x.x, y.y, gy);
-          }
+      for (int j = 0; j < CPL; ++j) {
+        if (j < jdot) {
+          const cplx x = xs[j * tpp], y = R[j];
+          al = fma(x.x, x.x, al);
+          al = fma(x.y, x.y, al);
+          be = fma(y.x, y.x, be);
+          be = fma(y.y, y.y, be);
+          gx = fma(x.x, y.x, gx);
+          gx = fma(x.y, y.y, gx);
+          gy = fma(x.y, y.x, gy);
+          gy = fma(-x.x, y.y, gy);
         }
       }
       for (int o = tpp >> 1; o > 0; o >>= 1) {
@@ -223,23 +243,18 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int ndot, int l
         const double g2 = gx * gx + gy * gy;
         const double ab = al * be;
         if (ab > 1e-280 && g2 > tol2 * ab) {
-          const double ag = sqrt(g2);
-          const double zeta = (be - al) / (2.0 * ag);
-          const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          const double cs = 1.0 / sqrt(1.0 + t * t);
-          const double sn = cs * t;
-          const double sx = sn * gx / ag, sy = sn * gy / ag;  // s e^{i phi}
+          double cs, sx, sy;
+          jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
-            const int c = tl + j * tpp;
-            if (c < len) {
-              const cplx x = xs[c], y = R[j];
+            if (j < jlen) {
+              const cplx x = xs[j * tpp], y = R[j];
               cplx xn, yn;
-              xn.x = cs * x.x - (sx * y.x - sy * y.y);
-              xn.y = cs * x.y - (sx * y.y + sy * y.x);
-              yn.x = cs * y.x + (sx * x.x + sy * x.y);
-              yn.y = cs * y.y + (sx * x.y - sy * x.x);
-              xs[c] = yn;  // the rows trade places
+              xn.x = fma(cs, x.x, fma(sy, y.y, -sx * y.x));
+              xn.y = fma(cs, x.y, -fma(sx, y.y, sy * y.x));
+              yn.x = fma(cs, y.x, fma(sx, x.x, sy * x.y));
+              yn.y = fma(cs, y.y, fma(sx, x.y, -sy * x.x));
+              xs[j * tpp] = yn;  // the rows trade places
               R[j] = xn;
             }
           }
@@ -247,10 +262,9 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int ndot, int l
         } else {
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
-            const int c = tl + j * tpp;
-            if (c < len) {
-              const cplx x = xs[c];
-              xs[c] = R[j];
+            if (j < jlen) {
+              const cplx x = xs[j * tpp];
+              xs[j * tpp] = R[j];
               R[j] = x;
             }
           }
@@ -266,42 +280,47 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int ndot, int l
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < CPL; ++j) {
-    const int c = tl + j * tpp;
-    if (team < no && c < len) Wg[(long)(2 * team + 1) * len + c] = R[j];
-  }
-  for (int idx = tid; idx < ne * len; idx += nt) {
-    const int r = idx / len, c = idx - r * len;
-    Wg[(long)(2 * r) * len + c] = S[idx];
+  for (int j = 0; j < CPL; ++j)
+    if (team < no && j < jlen) Wg[(long)(2 * team + 1) * ldw + tl + j * tpp] = R[j];
+  for (int idx = tid; idx < ne * ldw; idx += nt) {
+    const int r = idx / ldw, c = idx - r * ldw;
+    Wg[(long)(2 * r) * ldw + c] = S[idx];
   }
   __syncthreads();
   if (sweeps_out) *sweeps_out = sweeps;
   return conv;
 }
 
-// Dispatcher: the register-resident path when the matrix fits (rows <= 2 teams, <= 16
-// columns per lane, even rows fit the shared buffer), else the generic shared/L2 path.
-__device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndot, int len, cplx* Wsm, int cap_elems, int tpp_hint,
+// Can the register-resident path take an (nrows x ldw) problem?  (ldw already padded)
+__host__ __device__ inline bool jacobi_oe_fits(int nt, int nrows, int ldw, int cap_elems) {
+  const int tpp = jacobi_oe_tpp(nt, nrows);
+  if (nt / tpp < (nrows >> 1)) return false;
+  if (ldw % tpp) return false;
+  if (ldw / tpp > 16) return false;
+  return (long)((nrows + 1) >> 1) * ldw <= cap_elems;
+}
+
+// Dispatcher.  Wg: nrows x ldw (row stride ldw), first ndotp columns enter the Gram entries;
+// for the register path ldw and ndotp are multiples of jacobi_oe_tpp(nt, nrows) (zero padded).
+__device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, cplx* Wsm, int cap_elems, int tpp_hint,
                                        double tol2, int max_sweeps, double* red, int* sweeps_out) {
   if (nrows <= 1) {
     if (sweeps_out) *sweeps_out = 0;
     return true;
   }
   const int nt = blockDim.x;
-  const int need_teams = nrows >> 1;
-  int tpp = 32;
-  while (tpp > 1 && nt / tpp < need_teams) tpp >>= 1;
-  const int cpl = (len + tpp - 1) / tpp;
-  const long need_elems = (long)((nrows + 1) >> 1) * len;
-  if (nt / tpp >= need_teams && cpl <= 16 && need_elems <= cap_elems) {
-    if (cpl <= 2) return jacobi_rows_oe<2>(Wg, nrows, ndot, len, Wsm, tpp, tol2, max_sweeps, red, sweeps_out);
-    if (cpl <= 4) return jacobi_rows_oe<4>(Wg, nrows, ndot, len, Wsm, tpp, tol2, max_sweeps, red, sweeps_out);
-    if (cpl <= 8) return jacobi_rows_oe<8>(Wg, nrows, ndot, len, Wsm, tpp, tol2, max_sweeps, red, sweeps_out);
-    return jacobi_rows_oe<16>(Wg, nrows, ndot, len, Wsm, tpp, tol2, max_sweeps, red, sweeps_out);
+  if (jacobi_oe_fits(nt, nrows, ldw, cap_elems)) {
+    const int tpp = jacobi_oe_tpp(nt, nrows);
+    const int jlen = ldw / tpp, jdot = (ndotp + tpp - 1) / tpp;
+    const int s_off = (int)((char*)Wsm - QSP_SMEM_BASE()), r_off = (int)((char*)red - QSP_SMEM_BASE());
+    if (jlen <= 2) return jacobi_rows_oe<2>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out);
+    if (jlen <= 4) return jacobi_rows_oe<4>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out);
+    if (jlen <= 8) return jacobi_rows_oe<8>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out);
+    return jacobi_rows_oe<16>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out);
   }
-  int cap_rows = cap_elems / len;
+  int cap_rows = cap_elems / ldw;
   if (cap_rows < 2) cap_rows = 2;
   int t2 = tpp_hint;
-  while (t2 > 1 && t2 > ndot) t2 >>= 1;
-  return jacobi_rows(Wg, nrows, ndot, len, Wsm, cap_rows, t2, tol2, max_sweeps, red, sweeps_out);
+  while (t2 > 1 && t2 > ndotp) t2 >>= 1;
+  return jacobi_rows(Wg, nrows, ndotp, ldw, Wsm, cap_rows, t2, tol2, max_sweeps, red, sweeps_out);
 }

@@ -235,12 +235,13 @@ struct RCompressArgs {
   int cap_rows_elems;       // shared elements available for Jacobi rows
   int tpp;                  // lanes per Jacobi pair
   int max_sweeps;
+  long long* prof;          // optional [grid][8] cycle counters (qsp_set_profile_buffer), else null
 };
 
 // scratch (complex elements per CTA): Mg (Din x 2Dout), Wg (2Dout x (Din+2Dout)),
 // Vg (Dout x 2Dout), Cg (Din x Dout), f (2 x Dout)
 __host__ __device__ inline long rcompress_work_elems(int Din, int Dout) {
-  return (long)Din * 2 * Dout + (long)2 * Dout * (Din + 2 * Dout) + (long)Dout * 2 * Dout + (long)Din * Dout +
+  return (long)Din * 2 * Dout + (long)2 * Dout * (Din + 2 * Dout + 64) + (long)Dout * 2 * Dout + (long)Din * Dout +
          2L * Dout + 64;
 }
 // shared: Jacobi rows | gemm tiles (aliased onto the same area) + norms/perm + red
@@ -269,12 +270,16 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
 
   cplx* Mg = P.work + (long)blockIdx.x * P.work_stride;
   cplx* Wg = Mg + (long)Din * 2 * Dout;
-  cplx* Vg = Wg + (long)2 * Dout * (Din + 2 * Dout);
+  cplx* Vg = Wg + (long)2 * Dout * (Din + 2 * Dout + 64);
   cplx* Cg = Vg + (long)Dout * 2 * Dout;
   cplx* fg = Cg + (long)Din * Dout;  // two ping-pong vectors for the <0..0| amplitude
 
   const long sin = (long)Din * 2 * Din, sout = (long)Dout * 2 * Dout;
   const int kmax = (P.max_bond > 0) ? imin(P.max_bond, Dout) : Dout;
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tck = 0;
+#define QSP_TICK() (tck = qsp_clock())
+#define QSP_TOCK(slot) (pc[slot] += qsp_clock() - tck, tck = qsp_clock())
 
   for (int inst = blockIdx.x; inst < P.B; inst += gridDim.x) {
     const cplx* A = P.in + (long)inst * L * sin;
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       cplx* Oi = O + (long)i * sout;
       const int b = bi[i], ro = bi[i + 1];  // stored extents of site i
       const int c = 2 * rp;
+      QSP_TICK();
       // ---- M[(x,p),k] = sum_r A[x,p,r] C[r,k]   (C = identity at the last site) -----------
       if (i == L - 1) {
         for (int idx = tid; idx < 2 * b * rp; idx += nt) {
@@ -343,30 +349,46 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         __syncthreads();
         break;
       }
+      QSP_TOCK(0);
       // ---- Jacobi SVD of M (b x c) ----------------------------------------------------
       const bool modeC = b > c;  // more rows than columns: rotate the columns, accumulate J
       const int nrows = modeC ? c : b;
       const int ndot = modeC ? b : c;
-      const int len = modeC ? b + c : c;
+      // pad the Gram part and the whole row to a multiple of the team width (zero columns)
+      const int tq = jacobi_oe_tpp(nt, nrows);
+      const int ndotp = ((ndot + tq - 1) / tq) * tq;
+      int len = modeC ? ndotp + c : ndotp;
+      len = ((len + tq - 1) / tq) * tq;
+      if (!jacobi_oe_fits(nt, nrows, len, P.cap_rows_elems) && !modeC) len = c;  // generic path: no padding needed
+      const int joff = modeC ? ndotp : 0;  // first column of the appended identity
       if (modeC) {
-        // Wg = [ M^T | I ]  (c x (b + c))
+        // Wg = [ M^T 0 | I 0 ]  (c x len)
         for (int idx = tid; idx < c * len; idx += nt) {
           const int r = idx / len, cc = idx - r * len;
-          cplx v;
+          cplx v = cmake(0.0, 0.0);
           if (cc < b)
             v = Mg[(long)cc * c + r];
-          else
-            v = cmake((cc - b) == r ? 1.0 : 0.0, 0.0);
+          else if (cc >= joff && cc - joff == r)
+            v = cmake(1.0, 0.0);
           Wg[idx] = v;
         }
       } else {
-        for (int idx = tid; idx < b * c; idx += nt) Wg[idx] = Mg[idx];
+        for (int idx = tid; idx < b * len; idx += nt) {
+          const int r = idx / len, cc = idx - r * len;
+          Wg[idx] = (cc < c) ? Mg[(long)r * c + cc] : cmake(0.0, 0.0);
+        }
       }
       __syncthreads();
       if (P.cap_rows_elems / len < 2) st |= QSP_ST_BOND_OVERFLOW;
       const double tol = 4e-16 * sqrt((double)ndot);
-      if (!jacobi_svd_rows(Wg, nrows, ndot, len, Wsm, P.cap_rows_elems, P.tpp, tol * tol, P.max_sweeps, red, (int*)0))
+      QSP_TOCK(1);
+      int nsweeps = 0;
+      if (!jacobi_svd_rows(Wg, nrows, modeC ? ndotp : len, len, Wsm, P.cap_rows_elems, P.tpp, tol * tol, P.max_sweeps, red,
+                           &nsweeps))
         st |= QSP_ST_JACOBI_NOCONV;
+      QSP_TOCK(2);
+      pc[5] += nsweeps;
+      pc[6] += 1;
       // ---- singular values = row norms; rank them ---------------------------------------
       {
         const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
@@ -402,10 +424,11 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         for (int q = tid; q < P.nsv; q += nt) sv[q] = (q < nrows) ? norms[perm[q]] : 0.0;
       }
       // ---- Vh -> out site i (k x 2 x rp) and compact copy Vg (k x c); U s -> Cg (b x k) --
+      QSP_TOCK(3);
       if (modeC) {
         for (int idx = tid; idx < k * c; idx += nt) {
           const int q = idx / c, cc = idx - q * c;
-          const cplx v = cconj(Wg[(long)perm[q] * len + b + cc]);
+          const cplx v = cconj(Wg[(long)perm[q] * len + joff + cc]);
           const int p = cc / rp, kk = cc - p * rp;
           Oi[((long)q * 2 + p) * Dout + kk] = v;
           Vg[idx] = v;
@@ -429,6 +452,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         // U s = M Vh^H
         cta_zgemm(b, k, c, Mg, c, 1, false, Vg, 1, c, true, Cg, Dout, 1, false, tiles);
       }
+      QSP_TOCK(4);
       // ---- <0...0| amplitude: f_new[q] = sum_kk Vh[q,(0,kk)] f[kk] ---------------------------
       if (P.amp0) {
         const cplx* f = fg + fcur * Dout;
@@ -447,4 +471,8 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
     if (tid == 0 && P.status && st) P.status[inst] |= st;
     __syncthreads();
   }
+  if (P.prof && tid == 0)
+    for (int q = 0; q < 8; ++q) P.prof[(long)blockIdx.x * 8 + q] += pc[q];
+#undef QSP_TICK
+#undef QSP_TOCK
 }

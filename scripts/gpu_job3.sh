@@ -1,0 +1,4 @@
+CMD="python scripts/ncu_target.py 16 64 1 148"
+$CMD > gpurun_out/plain3.log 2>&1 && timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_right_compress -s 2 -c 1 -o gpurun_out/prof_rcompress_r1a $CMD > gpurun_out/ncu3.log 2>&1
+tail -3 gpurun_out/plain3.log gpurun_out/ncu3.log
+ls -la gpurun_out

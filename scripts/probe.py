@@ -19,3 +19,15 @@ for r in range(reps):
     torch.cuda.synchronize(); dt = time.time() - t0
     F = flop_model.flops_per_mps(L, chi, layers)["total"]
     print(f"L={L} chi={chi} layers={layers} B={B}: {dt:.3f}s  {B/dt:.2f} MPS/s  F_ref-equivalent {B*F/dt/1e12:.2f} TFLOP/s  status {res.status.unique().tolist()} |ov| mean {res.overlaps[layers-1].abs().mean().item():.3e} dis {res.dis_overlaps[layers-1].abs().mean().item():.3e}", flush=True)
+if os.environ.get("PROBE_PROF", "0") == "1":
+    import ctypes
+    prof = torch.zeros((4096, 8), dtype=torch.int64, device=dev)
+    eng.lib.qsp_set_profile_buffer(ctypes.c_void_p(prof.data_ptr()))
+    res = eng.seq_prepare(raw, b0, layers, max_bond=chi, encoded=False)
+    torch.cuda.synchronize()
+    eng.lib.qsp_set_profile_buffer(None)
+    p = prof.cpu().numpy().astype(float)
+    p = p[p[:, 6] > 0]
+    tot = p[:, :5].sum()
+    print("rcompress phases (share of cycles): gemm1 %.3f stage %.3f jacobi %.3f rank %.3f vh/us %.3f | sweeps/site %.2f | Mcycles per CTA %.1f" % (
+        *(p[:, :5].sum(0) / tot), p[:, 5].sum() / p[:, 6].sum(), p[:, :5].sum(1).mean() / 1e6))

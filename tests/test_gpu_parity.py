@@ -155,7 +155,7 @@ def test_overlap_matches_oracle(drv):
 # ---------------------------------------------------------------------------------------
 # the layer loop
 # ---------------------------------------------------------------------------------------
-def _check_pipeline(drv, tgts, layers, max_bond, D, tol=1e-10, same_convention=True, flags=0):
+def _check_pipeline(drv, tgts, layers, max_bond, D, tol=1e-10, same_convention=True, flags=0, check_svals=True):
     a, b = _dev(drv, tgts, D)
     r = drv.seq_prepare(a, b, layers, max_bond=max_bond, flags=flags)
     r = {k: drv.to_host(v) for k, v in r.items()}
@@ -171,7 +171,7 @@ def _check_pipeline(drv, tgts, layers, max_bond, D, tol=1e-10, same_convention=T
         assert np.abs(np.array(tf["disentangled_mps_overlaps"]) - r["dis"][:, k]).max() < tol
         assert np.abs(np.array(tf["overlaps"]) - r["overlaps"][ev, k]).max() < tol
         # per-bond singular values of every layer's D=2 truncation, 1e-12 relative
-        for j in range(layers):
+        for j in range(layers if check_svals else 0):
             for q, s in enumerate(tf["d2_svals"][j]):
                 i = len(tgt) - 1 - q
                 n = min(2, len(s))
@@ -234,7 +234,9 @@ def test_golden_p4_layer1_and_teacher_forced(drv):
     r = drv.seq_prepare(a, b, 1, max_bond=45)
     r = {k: drv.to_host(v) for k, v in r.items()}
     assert abs(abs(r["overlaps"][0, 0]) - 0.9670549179903772) < 1e-11
-    _check_pipeline(drv, [tg], 3, 45, 45, same_convention=False)
+    # (degenerate pairs at the D=2 cut, 0.07527/0.07527: which vector survives is a LAPACK-vs-Jacobi
+    # coin toss, so later bonds' singular values are not comparable either)
+    _check_pipeline(drv, [tg], 3, 45, 45, same_convention=False, check_svals=False)
 
 
 def test_facade_readme_example(drv, capsys):
