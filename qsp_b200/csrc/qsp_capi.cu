@@ -331,14 +331,15 @@ extern "C" int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, i
 // the layer loop
 // ------------------------------------------------------------------------------------
 struct SeqPlan {
-  int De;  // padded bond of the encoded state
+  int De;   // padded bond of the encoded state: 2^min(layers, L/2)
+  int De2;  // padded bond of its doubled intermediate: 2^min(layers, L/2 + 1)
   size_t off_psi, off_psib, off_psi2, off_psi2b, off_d2, off_d2b, off_tmp, off_tmpb;
   size_t off_enc, off_encb, off_enc2, off_enc2b, off_zero, off_zerob, off_scratch;
   size_t scratch_bytes, total;
   bool ok;
 };
-static int enc_pad(int L, int layers) {
-  int cap = L / 2;
+static int enc_pad(int L, int layers, int extra) {
+  int cap = L / 2 + extra;
   int e = layers < cap ? layers : cap;
   if (e > 20) e = 20;
   return 1 << e;
@@ -350,7 +351,8 @@ static SeqPlan plan_seq(int B, int L, int D, int layers, int max_bond, int flags
   p.ok = true;
   const bool enc = !(flags & QSP_FLAG_NO_ENCODED);
   const bool second = (flags & QSP_FLAG_SECOND_PASS) != 0;
-  p.De = enc ? enc_pad(L, layers) : 1;
+  p.De = enc ? enc_pad(L, layers, 0) : 1;
+  p.De2 = enc ? enc_pad(L, layers, 1) : 1;
   size_t o = 0;
   p.off_psi = o, o += mps_bytes(B, L, D);
   p.off_psib = o, o += bonds_bytes(B, L);
@@ -380,10 +382,12 @@ static SeqPlan plan_seq(int B, int L, int D, int layers, int max_bond, int flags
   if (enc) {
     p.off_enc = o, o += mps_bytes(B, L, p.De);
     p.off_encb = o, o += bonds_bytes(B, L);
-    p.off_enc2 = o, o += mps_bytes(B, L, 2 * p.De);
+    // after j layers the encoded state has bonds <= min(2^j, 2^(L/2)), so the doubled
+    // intermediate of any application is <= min(2^layers, 2^(L/2+1)) = De2
+    p.off_enc2 = o, o += mps_bytes(B, L, p.De2);
     p.off_enc2b = o, o += bonds_bytes(B, L);
-    if (!plan_lcanon(2 * p.De, d, &lp)) p.ok = false;
-    t = qsp_right_compress_workspace_bytes(B, L, 2 * p.De, p.De);
+    if (!plan_lcanon(p.De2, d, &lp)) p.ok = false;
+    t = qsp_right_compress_workspace_bytes(B, L, p.De2, p.De);
     if (!t) p.ok = false;
     s = t > s ? t : s;
     t = qsp_overlap_workspace_bytes(B, L, p.De, D);
@@ -442,7 +446,7 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
   int32_t* enc2b = (int32_t*)(w + p.off_enc2b);
   void* scratch = w + p.off_scratch;
   const size_t sb = p.scratch_bytes;
-  const int De = p.De;
+  const int De = p.De, De2 = p.De2;
   int rc;
 
   dev_copy(psi, target, (size_t)B * L * D * 2 * D * sizeof(cplx), st);
@@ -482,10 +486,10 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
       for (int k = it; k >= 0; --k) {
         const qsp_c128* Gk = G + (size_t)k * B * L * 16;
         const int32_t* kk = kind + (size_t)k * B * L;
-        if ((rc = qsp_apply_forward_layer(enc, encb, De, Gk, kk, enc2, enc2b, 2 * De, B, L, status, stream)))
+        if ((rc = qsp_apply_forward_layer(enc, encb, De, Gk, kk, enc2, enc2b, De2, B, L, status, stream)))
           return rc;
-        if ((rc = qsp_left_canonize(enc2, enc2b, B, L, 2 * De, status, stream))) return rc;
-        if ((rc = qsp_right_compress(enc2, enc2b, 2 * De, enc, encb, De, B, L, 0, cutoff, k == 0 ? 1 : 0, nullptr, 0,
+        if ((rc = qsp_left_canonize(enc2, enc2b, B, L, De2, status, stream))) return rc;
+        if ((rc = qsp_right_compress(enc2, enc2b, De2, enc, encb, De, B, L, 0, cutoff, k == 0 ? 1 : 0, nullptr, 0,
                                      nullptr, status, scratch, sb, stream)))
           return rc;
       }

@@ -172,10 +172,30 @@ __device__ inline bool jacobi_rows(cplx* Wg, int nrows, int ndot, int len, cplx*
 // tpp columns (ldw = jlen*tpp) and the Gram part to jdot*tpp columns, so the column loops
 // are branch-free and warp-uniform.
 // ----------------------------------------------------------------------------------
-__host__ __device__ inline int jacobi_oe_tpp(int nt, int nrows) {
+#define QSP_JPAD 32
+// A sweep whose largest rotated |g|/sqrt(alpha beta) is <= QSP_JAC_QUAD leaves off-diagonals of
+// order n * QSP_JAC_QUAD^2 ~ 1e-16 (quadratic convergence): no verification sweep is needed.
+#define QSP_JAC_QUAD 1e-9  // rows are zero-padded to a multiple of this many columns
+
+// Team geometry for an (nrows x ldw) problem (ldw a multiple of QSP_JPAD): tpp lanes per team,
+// np pairs per team, cpl = ldw / tpp columns per lane (<= 16; up to 8 both rows of a visit are
+// held in registers, beyond that the shared row is read twice).  Returns false when the register path cannot take the problem.
+__host__ __device__ inline bool jacobi_oe_geometry(int nt, int nrows, int ldw, int* tpp_out, int* np_out) {
+  const int pairs = nrows >> 1;
+  if (ldw % QSP_JPAD) return false;
   int tpp = 32;
-  while (tpp > 1 && nt / tpp < (nrows >> 1)) tpp >>= 1;
-  return tpp;
+  while (tpp > 1 && nt / tpp < pairs) tpp >>= 1;  // one pair per team when possible
+  int np = 1;
+  if (nt / tpp < pairs) return false;
+  while (ldw / tpp > 16 || ldw % tpp) {  // too many columns per lane: widen the team, two pairs per team
+    if (tpp == 32) return false;
+    tpp <<= 1;
+  }
+  while ((nt / tpp) * np < pairs) ++np;
+  if (np > 2 || (np == 2 && ldw / tpp > 8)) return false;
+  *tpp_out = tpp;
+  *np_out = np;
+  return true;
 }
 
 // rotation parameters from the Gram entries: x' = cs x - se y, y' = conj(se) x + cs y
@@ -192,7 +212,7 @@ __device__ __forceinline__ void jacobi_rotation(double al, double be, double gx,
   sy = cw * gy;
 }
 
-template <int CPL>
+template <int CPL, int NP, bool HOLD>
 __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int jlen, int s_off, int tpp, double tol2,
                                             int max_sweeps, int red_off, int* sweeps_out) {
   cplx* S = (cplx*)(QSP_SMEM_BASE() + s_off);
@@ -201,10 +221,14 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
   const int team = tid / tpp, tl = tid % tpp;
   const int ldw = jlen * tpp;
   const int ne = (nrows + 1) >> 1, no = nrows >> 1;
-  cplx R[CPL];
+  cplx R[NP][CPL];
 #pragma unroll
-  for (int j = 0; j < CPL; ++j)
-    R[j] = (team < no && j < jlen) ? Wg[(long)(2 * team + 1) * ldw + tl + j * tpp] : cmake(0.0, 0.0);
+  for (int q = 0; q < NP; ++q) {
+    const int p = team * NP + q;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+      R[q][j] = (p < no && j < jlen) ? Wg[(long)(2 * p + 1) * ldw + tl + j * tpp] : cmake(0.0, 0.0);
+  }
   for (int idx = tid; idx < ne * ldw; idx += nt) {
     const int r = idx / ldw, c = idx - r * ldw;
     S[idx] = Wg[(long)(2 * r) * ldw + c];
@@ -212,60 +236,74 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
   __syncthreads();
   bool conv = false;
   int sweeps = 0;
+  volatile int* flag = (volatile int*)(red + 48);  // set when a rotation above QSP_JAC_QUAD happened
   while (sweeps < max_sweeps) {
-    int nrot = 0;
+    if (tid == 0) *flag = 0;
+    __syncthreads();
     for (int r = 0; r < nrows; ++r) {
-      const int slot = team + (r & 1);
-      const bool valid = (team < no) && (slot < ne);
-      cplx* xs = S + (long)(valid ? slot : 0) * ldw + tl;
-      double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
 #pragma unroll
-      for (int j = 0; j < CPL; ++j) {
-        if (j < jdot) {
-          const cplx x = xs[j * tpp], y = R[j];
-          al = fma(x.x, x.x, al);
-          al = fma(x.y, x.y, al);
-          be = fma(y.x, y.x, be);
-          be = fma(y.y, y.y, be);
-          gx = fma(x.x, y.x, gx);
-          gx = fma(x.y, y.y, gx);
-          gy = fma(x.y, y.x, gy);
-          gy = fma(-x.x, y.y, gy);
+      for (int q = 0; q < NP; ++q) {
+        const int p = team * NP + q;
+        const int slot = p + (r & 1);
+        const bool valid = (p < no) && (slot < ne);
+        cplx* xs = S + (long)(valid ? slot : 0) * ldw + tl;
+        cplx x[HOLD ? CPL : 1];
+        if (HOLD) {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j)
+            if (j < jlen) x[HOLD ? j : 0] = xs[j * tpp];
         }
-      }
-      for (int o = tpp >> 1; o > 0; o >>= 1) {
-        al += shfl_xor_d(al, o);
-        be += shfl_xor_d(be, o);
-        gx += shfl_xor_d(gx, o);
-        gy += shfl_xor_d(gy, o);
-      }
-      if (valid) {
-        const double g2 = gx * gx + gy * gy;
-        const double ab = al * be;
-        if (ab > 1e-280 && g2 > tol2 * ab) {
-          double cs, sx, sy;
-          jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
+        double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) {
-            if (j < jlen) {
-              const cplx x = xs[j * tpp], y = R[j];
-              cplx xn, yn;
-              xn.x = fma(cs, x.x, fma(sy, y.y, -sx * y.x));
-              xn.y = fma(cs, x.y, -fma(sx, y.y, sy * y.x));
-              yn.x = fma(cs, y.x, fma(sx, x.x, sy * x.y));
-              yn.y = fma(cs, y.y, fma(sx, x.y, -sy * x.x));
-              xs[j * tpp] = yn;  // the rows trade places
-              R[j] = xn;
-            }
+        for (int j = 0; j < CPL; ++j) {
+          if (j < jdot) {
+            const cplx y = R[q][j];
+            const cplx xv = HOLD ? x[HOLD ? j : 0] : xs[j * tpp];
+            al = fma(xv.x, xv.x, al);
+            al = fma(xv.y, xv.y, al);
+            be = fma(y.x, y.x, be);
+            be = fma(y.y, y.y, be);
+            gx = fma(xv.x, y.x, gx);
+            gx = fma(xv.y, y.y, gx);
+            gy = fma(xv.y, y.x, gy);
+            gy = fma(-xv.x, y.y, gy);
           }
-          if (tl == 0) ++nrot;
-        } else {
+        }
+        for (int o = tpp >> 1; o > 0; o >>= 1) {
+          al += shfl_xor_d(al, o);
+          be += shfl_xor_d(be, o);
+          gx += shfl_xor_d(gx, o);
+          gy += shfl_xor_d(gy, o);
+        }
+        if (valid) {
+          const double g2 = gx * gx + gy * gy;
+          const double ab = al * be;
+          if (ab > 1e-280 && g2 > tol2 * ab) {
+            double cs, sx, sy;
+            jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
+            if (tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) *flag = 1;
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) {
-            if (j < jlen) {
-              const cplx x = xs[j * tpp];
-              xs[j * tpp] = R[j];
-              R[j] = x;
+            for (int j = 0; j < CPL; ++j) {
+              if (j < jlen) {
+                const cplx y = R[q][j];
+                const cplx xv = HOLD ? x[HOLD ? j : 0] : xs[j * tpp];
+                cplx xn, yn;
+                xn.x = fma(cs, xv.x, fma(sy, y.y, -sx * y.x));
+                xn.y = fma(cs, xv.y, -fma(sx, y.y, sy * y.x));
+                yn.x = fma(cs, y.x, fma(sx, xv.x, sy * xv.y));
+                yn.y = fma(cs, y.y, fma(sx, xv.y, -sy * xv.x));
+                xs[j * tpp] = yn;  // the rows trade places
+                R[q][j] = xn;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+              if (j < jlen) {
+                const cplx xv = HOLD ? x[HOLD ? j : 0] : xs[j * tpp];
+                xs[j * tpp] = R[q][j];
+                R[q][j] = xv;
+              }
             }
           }
         }
@@ -273,15 +311,20 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
       __syncthreads();
     }
     ++sweeps;
-    if ((int)(block_sum((double)nrot, red) + 0.5) == 0) {
+    if (*flag == 0) {  // (the round loop ended with a barrier)
       conv = true;
       break;
     }
+    __syncthreads();
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < CPL; ++j)
-    if (team < no && j < jlen) Wg[(long)(2 * team + 1) * ldw + tl + j * tpp] = R[j];
+  for (int q = 0; q < NP; ++q) {
+    const int p = team * NP + q;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+      if (p < no && j < jlen) Wg[(long)(2 * p + 1) * ldw + tl + j * tpp] = R[q][j];
+  }
   for (int idx = tid; idx < ne * ldw; idx += nt) {
     const int r = idx / ldw, c = idx - r * ldw;
     Wg[(long)(2 * r) * ldw + c] = S[idx];
@@ -293,15 +336,13 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
 
 // Can the register-resident path take an (nrows x ldw) problem?  (ldw already padded)
 __host__ __device__ inline bool jacobi_oe_fits(int nt, int nrows, int ldw, int cap_elems) {
-  const int tpp = jacobi_oe_tpp(nt, nrows);
-  if (nt / tpp < (nrows >> 1)) return false;
-  if (ldw % tpp) return false;
-  if (ldw / tpp > 16) return false;
+  int tpp, np;
+  if (!jacobi_oe_geometry(nt, nrows, ldw, &tpp, &np)) return false;
   return (long)((nrows + 1) >> 1) * ldw <= cap_elems;
 }
 
 // Dispatcher.  Wg: nrows x ldw (row stride ldw), first ndotp columns enter the Gram entries;
-// for the register path ldw and ndotp are multiples of jacobi_oe_tpp(nt, nrows) (zero padded).
+// for the register path ldw and ndotp are multiples of QSP_JPAD (zero padded).
 __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, cplx* Wsm, int cap_elems, int tpp_hint,
                                        double tol2, int max_sweeps, double* red, int* sweeps_out) {
   if (nrows <= 1) {
@@ -309,14 +350,22 @@ __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, 
     return true;
   }
   const int nt = blockDim.x;
-  if (jacobi_oe_fits(nt, nrows, ldw, cap_elems)) {
-    const int tpp = jacobi_oe_tpp(nt, nrows);
+  int tpp, np;
+  if (jacobi_oe_geometry(nt, nrows, ldw, &tpp, &np) && (long)((nrows + 1) >> 1) * ldw <= cap_elems) {
     const int jlen = ldw / tpp, jdot = (ndotp + tpp - 1) / tpp;
     const int s_off = (int)((char*)Wsm - QSP_SMEM_BASE()), r_off = (int)((char*)red - QSP_SMEM_BASE());
-    if (jlen <= 2) return jacobi_rows_oe<2>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out);
-    if (jlen <= 4) return jacobi_rows_oe<4>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out);
-    if (jlen <= 8) return jacobi_rows_oe<8>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out);
-    return jacobi_rows_oe<16>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out);
+#define QSP_OE(C, N, H) \
+  jacobi_rows_oe<C, N, H>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
+    if (np == 1) {
+      if (jlen <= 2) return QSP_OE(2, 1, true);
+      if (jlen <= 4) return QSP_OE(4, 1, true);
+      if (jlen <= 8) return QSP_OE(8, 1, true);
+      return QSP_OE(16, 1, false);
+    }
+    if (jlen <= 4) return QSP_OE(4, 2, true);
+    if (jlen <= 8) return QSP_OE(8, 2, false);
+    return false;  // unreachable: geometry limits np = 2 to 8 columns per lane
+#undef QSP_OE
   }
   int cap_rows = cap_elems / ldw;
   if (cap_rows < 2) cap_rows = 2;

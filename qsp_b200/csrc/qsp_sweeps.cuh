@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       const int nrows = modeC ? c : b;
       const int ndot = modeC ? b : c;
       // pad the Gram part and the whole row to a multiple of the team width (zero columns)
-      const int tq = jacobi_oe_tpp(nt, nrows);
+      const int tq = QSP_JPAD;
       const int ndotp = ((ndot + tq - 1) / tq) * tq;
       int len = modeC ? ndotp + c : ndotp;
       len = ((len + tq - 1) / tq) * tq;
