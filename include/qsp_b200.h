@@ -131,6 +131,11 @@ int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bonds, int B, 
  * [3] ranking, [4] Vh/U s, [5] Jacobi sweeps, [6] sites.  NULL (default) disables it. */
 void qsp_set_profile_buffer(void* buf);
 
+/* Development aid: Jacobi micro-benchmark, W[B][nrows][ldw] orthogonalised in place (ldw a
+ * multiple of 32), nt threads per CTA. */
+void qsp_jacobi_variant(int bits); /* timing experiments: disables parts of the Jacobi round (results invalid) */
+int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int nt, int* sweeps, int* ok, void* stream);
+
 /* Measurement aid: blocks x threads threads each run `iters` rounds of 16 independent
  * double-precision FMAs (flops = blocks*threads*iters*32).  bench.py times it to obtain the
  * FP64 roofline denominator, which MEASURED_PEAKS.json does not carry. */

@@ -97,8 +97,13 @@ struct LCanonPlan {
   size_t smem;
 };
 static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
-  p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : 256);
+  if (2 * D > 32 * QSP_QR_MAXR) return false;  // a column must fit one warp's registers
+  p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : (D <= 48 ? 256 : 512));
   p->smem = lcanon_smem_bytes(D, p->nt);
+  if (p->smem > d.max_smem && p->nt == 512) {
+    p->nt = 256;
+    p->smem = lcanon_smem_bytes(D, p->nt);
+  }
   return p->smem <= d.max_smem;
 }
 
@@ -155,7 +160,7 @@ extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, in
   if (!plan_lcanon(D, d, &p)) return QSP_ERR_UNSUPPORTED;
   QSP_PREP_KERNEL(k_left_canon, p.smem);
   int grid = grid_for(B, blocks_per_sm((const void*)k_left_canon, p.nt, p.smem), d);
-  QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, D, status);
+  QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, D, status, g_prof);
   ++g_launches;
   return check_launch();
 }
@@ -291,6 +296,53 @@ __global__ void k_dfma_probe(double* out, int iters) {
 extern "C" int qsp_dfma_probe(double* out, int blocks, int threads, int iters, void* stream) {
   if (!out || blocks <= 0 || threads <= 0 || threads % 32) return QSP_ERR_ARG;
   QSP_LAUNCH(k_dfma_probe, blocks, threads, 0, (qsp_stream_t)stream, out, iters);
+  ++g_launches;
+  return check_launch();
+}
+
+// Jacobi micro-benchmark (development aid): every CTA orthogonalises its own copy of an
+// nrows x ldw matrix (W[B][nrows][ldw]) in place; sweeps[B] receives the sweep counts.
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX) k_jacobi_bench(cplx* W, int nrows, int ndotp, int ldw, int B, int cap_elems,
+                                                        int* sweeps, int* ok) {
+  char* sm = QSP_SMEM_BASE();
+  cplx* Wsm = (cplx*)sm;
+  double* red = (double*)(sm + (size_t)cap_elems * sizeof(cplx));
+  for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    int ns = 0;
+    const double tol = 4e-16 * sqrt((double)ndotp);
+    bool c = jacobi_svd_rows(W + (long)inst * nrows * ldw, nrows, ndotp, ldw, Wsm, cap_elems, 8, tol * tol, 60, red, &ns);
+    if (threadIdx.x == 0) {
+      sweeps[inst] = ns;
+      ok[inst] = c ? 1 : 0;
+    }
+    __syncthreads();
+  }
+}
+extern "C" void qsp_jacobi_variant(int v) {
+#ifdef QSP_JACOBI_ABLATION
+  cudaMemcpyToSymbol(g_jvar, &v, sizeof(int));
+#else
+  (void)v;
+#endif
+}
+extern "C" int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int nt, int* sweeps, int* ok,
+                                void* stream) {
+  DevInfo d = dev_info();
+  long cap = ((long)d.max_smem - 1024) / (long)sizeof(cplx);
+  long need = (long)nrows * ldw;
+  if (need < cap) cap = need;
+  size_t smem = (size_t)cap * sizeof(cplx) + 64 * sizeof(double) + 64;
+  int grid = B < d.sms ? B : d.sms;
+  if (nt > 512) {
+    QSP_PREP_KERNEL(k_jacobi_bench<1024>, smem);
+    QSP_LAUNCH(k_jacobi_bench<1024>, grid, nt, smem, (qsp_stream_t)stream, (cplx*)W, nrows, ndotp, ldw, B, (int)cap, sweeps,
+               ok);
+  } else {
+    QSP_PREP_KERNEL(k_jacobi_bench<512>, smem);
+    QSP_LAUNCH(k_jacobi_bench<512>, grid, nt, smem, (qsp_stream_t)stream, (cplx*)W, nrows, ndotp, ldw, B, (int)cap, sweeps,
+               ok);
+  }
   ++g_launches;
   return check_launch();
 }

@@ -172,6 +172,15 @@ __device__ inline bool jacobi_rows(cplx* Wg, int nrows, int ndot, int len, cplx*
 // tpp columns (ldw = jlen*tpp) and the Gram part to jdot*tpp columns, so the column loops
 // are branch-free and warp-uniform.
 // ----------------------------------------------------------------------------------
+// Ablation switches for timing experiments (scripts/jacobi_bench.py, results invalid when set):
+// bit0 no dot, bit1 no shuffles, bit2 no scalar chain, bit3 no rotation update, bit4 no barrier.
+// Compiled in only with -DQSP_JACOBI_ABLATION; the product build folds them away.
+#ifdef QSP_JACOBI_ABLATION
+__device__ int g_jvar = 0;
+#define QSP_JV() (g_jvar)
+#else
+#define QSP_JV() (0)
+#endif
 #define QSP_JPAD 32
 // A sweep whose largest rotated |g|/sqrt(alpha beta) is <= QSP_JAC_QUAD leaves off-diagonals of
 // order n * QSP_JAC_QUAD^2 ~ 1e-16 (quadratic convergence): no verification sweep is needed.
@@ -237,6 +246,7 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
   bool conv = false;
   int sweeps = 0;
   volatile int* flag = (volatile int*)(red + 48);  // set when a rotation above QSP_JAC_QUAD happened
+  const int jv = QSP_JV();
   while (sweeps < max_sweeps) {
     if (tid == 0) *flag = 0;
     __syncthreads();
@@ -256,7 +266,7 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
         double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-          if (j < jdot) {
+          if (j < jdot && !(jv & 1)) {
             const cplx y = R[q][j];
             const cplx xv = HOLD ? x[HOLD ? j : 0] : xs[j * tpp];
             al = fma(xv.x, xv.x, al);
@@ -269,18 +279,22 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
             gy = fma(-xv.x, y.y, gy);
           }
         }
-        for (int o = tpp >> 1; o > 0; o >>= 1) {
-          al += shfl_xor_d(al, o);
-          be += shfl_xor_d(be, o);
-          gx += shfl_xor_d(gx, o);
-          gy += shfl_xor_d(gy, o);
-        }
+        if (!(jv & 2))
+          for (int o = tpp >> 1; o > 0; o >>= 1) {
+            al += shfl_xor_d(al, o);
+            be += shfl_xor_d(be, o);
+            gx += shfl_xor_d(gx, o);
+            gy += shfl_xor_d(gy, o);
+          }
         if (valid) {
           const double g2 = gx * gx + gy * gy;
           const double ab = al * be;
-          if (ab > 1e-280 && g2 > tol2 * ab) {
+          if ((jv & 8) ? false : ((jv & 4) ? true : (ab > 1e-280 && g2 > tol2 * ab))) {
             double cs, sx, sy;
-            jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
+            if (jv & 4) {
+              cs = 0.8, sx = 0.6, sy = 0.0;
+            } else
+              jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
             if (tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) *flag = 1;
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
@@ -308,9 +322,14 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
           }
         }
       }
-      __syncthreads();
+      if (!(jv & 16)) __syncthreads();
     }
     ++sweeps;
+    if (jv) {
+      __syncthreads();
+      if (sweeps >= 8) break;
+      continue;
+    }
     if (*flag == 0) {  // (the round loop ended with a barrier)
       conv = true;
       break;

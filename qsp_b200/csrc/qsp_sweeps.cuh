@@ -38,59 +38,90 @@ __host__ __device__ inline size_t lcanon_smem_bytes(int Dm, int nt) {
 // Householder QR of S (m x n, column-major, column stride ldS) in place.  On return the
 // leading K = min(m,n) columns of S hold the thin Q and R (K x n, row-major, stride ldR)
 // holds the triangular factor with a non-negative real diagonal.
+//
+// A warp owns a column while it is updated: the reflector (rows j..m-1 of column j, v_j = 1)
+// and the column both sit in registers (QSP_QR_MAXR rows per lane, m - j <= 32*QSP_QR_MAXR),
+// so a column is read and written once per reflector; the warp that finishes column j+1
+// immediately builds reflector j+1 (look-ahead), so there is one barrier per reflector.
+#define QSP_QR_MAXR 8
+
+// reflector from column `col` (rows j..m-1): writes the scaled v below the diagonal, tau, beta.
+__device__ __forceinline__ void qr_make_reflector(cplx* col, int j, int m, int lane, cplx* tau, double* beta) {
+  double xn2 = 0.0;
+  for (int r = j + 1 + lane; r < m; r += 32) xn2 += cabs2(col[r]);
+  for (int o = 16; o > 0; o >>= 1) xn2 += shfl_xor_d(xn2, o);
+  const cplx alpha = col[j];
+  cplx t;
+  double bt;
+  if (xn2 == 0.0 && alpha.y == 0.0) {
+    t = cmake(0.0, 0.0);
+    bt = alpha.x;
+  } else {
+    const double nrm = sqrt(cabs2(alpha) + xn2);
+    bt = alpha.x >= 0.0 ? -nrm : nrm;
+    t = cmake((bt - alpha.x) / bt, -alpha.y / bt);
+    const cplx sc = cdiv(cmake(1.0, 0.0), cmake(alpha.x - bt, alpha.y));
+    for (int r = j + 1 + lane; r < m; r += 32) col[r] = cmul(col[r], sc);
+  }
+  if (lane == 0) {
+    tau[j] = t;
+    beta[j] = bt;
+  }
+  __syncwarp();
+}
+
+// col <- (I - f v v^H) col on rows j..m-1, v held in registers (vr), v_j = 1.
+__device__ __forceinline__ void qr_apply_reflector(const cplx* vr, cplx* colc, int j, int m, int lane, cplx f) {
+  cplx cr[QSP_QR_MAXR];
+  cplx w = cmake(0.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < QSP_QR_MAXR; ++k) {
+    const int r = j + lane + 32 * k;
+    if (r < m) {
+      cr[k] = colc[r];
+      cfma_conja(w, vr[k], cr[k]);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    w.x += shfl_xor_d(w.x, o);
+    w.y += shfl_xor_d(w.y, o);
+  }
+  const cplx g = cmul(f, w);
+#pragma unroll
+  for (int k = 0; k < QSP_QR_MAXR; ++k) {
+    const int r = j + lane + 32 * k;
+    if (r < m) colc[r] = csub(cr[k], cmul(g, vr[k]));
+  }
+}
+
 __device__ inline void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
-                                          double* red) {
+                                          long long* pc) {
+  long long tck = qsp_clock();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int K = imin(m, n);
+  if (warp == 0) qr_make_reflector(S, 0, m, lane, tau, beta);
+  __syncthreads();
   for (int j = 0; j < K; ++j) {
-    cplx* colj = S + (long)j * ldS;
-    // ---- reflector j (warp 0) -------------------------------------------------------
-    if (warp == 0) {
-      double xn2 = 0.0;
-      for (int r = j + 1 + lane; r < m; r += 32) xn2 += cabs2(colj[r]);
-      for (int o = 16; o > 0; o >>= 1) xn2 += shfl_xor_d(xn2, o);
-      const cplx alpha = colj[j];
-      cplx t;
-      double bt;
-      if (xn2 == 0.0 && alpha.y == 0.0) {
-        t = cmake(0.0, 0.0);
-        bt = alpha.x;
-      } else {
-        const double nrm = sqrt(cabs2(alpha) + xn2);
-        bt = alpha.x >= 0.0 ? -nrm : nrm;
-        t = cmake((bt - alpha.x) / bt, -alpha.y / bt);
-        const cplx sc = cdiv(cmake(1.0, 0.0), cmake(alpha.x - bt, alpha.y));
-        for (int r = j + 1 + lane; r < m; r += 32) colj[r] = cmul(colj[r], sc);
-      }
-      if (lane == 0) {
-        tau[j] = t;
-        beta[j] = bt;
-      }
-    }
-    __syncthreads();
-    // ---- apply H_j^H = I - conj(tau) v v^H to the trailing columns ----------------------
+    const cplx* colj = S + (long)j * ldS;
     const cplx tj = tau[j];
-    if (tj.x != 0.0 || tj.y != 0.0) {
-      for (int c = j + 1 + warp; c < n; c += nw) {
-        cplx* colc = S + (long)c * ldS;
-        cplx w = cmake(0.0, 0.0);
-        for (int r = j + lane; r < m; r += 32) {
-          cplx v = (r == j) ? cmake(1.0, 0.0) : colj[r];
-          cfma_conja(w, v, colc[r]);
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          w.x += shfl_xor_d(w.x, o);
-          w.y += shfl_xor_d(w.y, o);
-        }
-        const cplx f = cmul(cconj(tj), w);
-        for (int r = j + lane; r < m; r += 32) {
-          cplx v = (r == j) ? cmake(1.0, 0.0) : colj[r];
-          colc[r] = csub(colc[r], cmul(f, v));
-        }
+    cplx vr[QSP_QR_MAXR];
+#pragma unroll
+    for (int k = 0; k < QSP_QR_MAXR; ++k) {
+      const int r = j + lane + 32 * k;
+      vr[k] = (r == j) ? cmake(1.0, 0.0) : (r < m ? colj[r] : cmake(0.0, 0.0));
+    }
+    // apply H_j^H = I - conj(tau) v v^H to the trailing columns; look-ahead on column j+1
+    for (int c = j + 1 + warp; c < n; c += nw) {
+      cplx* colc = S + (long)c * ldS;
+      if (tj.x != 0.0 || tj.y != 0.0) qr_apply_reflector(vr, colc, j, m, lane, cconj(tj));
+      if (c == j + 1 && j + 1 < K) {
+        __syncwarp();
+        qr_make_reflector(colc, j + 1, m, lane, tau, beta);
       }
     }
     __syncthreads();
   }
+  pc[1] += qsp_clock() - tck, tck = qsp_clock();
   // ---- R out (upper trapezoid, diagonal = beta), sign-fixed --------------------------
   for (int idx = tid; idx < K * n; idx += blockDim.x) {
     const int r = idx / n, c = idx - r * n;
@@ -103,28 +134,19 @@ __device__ inline void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* 
     R[(long)r * ldR + c] = v;
   }
   __syncthreads();
+  pc[2] += qsp_clock() - tck, tck = qsp_clock();
   // ---- thin Q in place (zung2r) ---------------------------------------------------------
   for (int j = K - 1; j >= 0; --j) {
     cplx* colj = S + (long)j * ldS;
     const cplx tj = tau[j];
     if (tj.x != 0.0 || tj.y != 0.0) {
-      for (int c = j + 1 + warp; c < K; c += nw) {
-        cplx* colc = S + (long)c * ldS;
-        cplx w = cmake(0.0, 0.0);
-        for (int r = j + lane; r < m; r += 32) {
-          cplx v = (r == j) ? cmake(1.0, 0.0) : colj[r];
-          cfma_conja(w, v, colc[r]);
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          w.x += shfl_xor_d(w.x, o);
-          w.y += shfl_xor_d(w.y, o);
-        }
-        const cplx f = cmul(tj, w);
-        for (int r = j + lane; r < m; r += 32) {
-          cplx v = (r == j) ? cmake(1.0, 0.0) : colj[r];
-          colc[r] = csub(colc[r], cmul(f, v));
-        }
+      cplx vr[QSP_QR_MAXR];
+#pragma unroll
+      for (int k = 0; k < QSP_QR_MAXR; ++k) {
+        const int r = j + lane + 32 * k;
+        vr[k] = (r == j) ? cmake(1.0, 0.0) : (r < m ? colj[r] : cmake(0.0, 0.0));
       }
+      for (int c = j + 1 + warp; c < K; c += nw) qr_apply_reflector(vr, S + (long)c * ldS, j, m, lane, tj);
     }
     __syncthreads();
     const double sg = beta[j] < 0.0 ? -1.0 : 1.0;
@@ -140,12 +162,12 @@ __device__ inline void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* 
     }
     __syncthreads();
   }
-  // columns j+1.. were finished with their own sign before column j touched them only
-  // from the left (H_j), which commutes with the column scaling: nothing left to fix.
+  pc[3] += qsp_clock() - tck;
 }
 
-__global__ void __launch_bounds__(256) k_left_canon(cplx* __restrict__ mps, int32_t* __restrict__ bonds, int B, int L, int D, int Dm,
-                             int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(512) k_left_canon(cplx* __restrict__ mps, int32_t* __restrict__ bonds, int B, int L, int D, int Dm,
+                             int32_t* __restrict__ status, long long* prof) {
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   char* sm = QSP_SMEM_BASE();
   const int ldS = 2 * Dm + 1;
   cplx* S = (cplx*)sm;
@@ -173,6 +195,7 @@ __global__ void __launch_bounds__(256) k_left_canon(cplx* __restrict__ mps, int3
       cplx* Ai = A + (long)i * site_stride;
       const int b = bd[i + 1];
       const int m = 2 * a, n = b;
+      long long tck = qsp_clock();
       if (i == 0) {
         for (int idx = tid; idx < m * n; idx += nt) {
           const int r = idx / n, c = idx - r * n;
@@ -194,7 +217,10 @@ __global__ void __launch_bounds__(256) k_left_canon(cplx* __restrict__ mps, int3
         break;
       }
       __syncthreads();
-      cta_householder_qr(S, m, n, ldS, R, Dm, tau, beta, red);
+      pc[0] += qsp_clock() - tck;
+      cta_householder_qr(S, m, n, ldS, R, Dm, tau, beta, pc);
+      tck = qsp_clock();
+      pc[6] += 1;
       const int K = imin(m, n);
       for (int idx = tid; idx < m * K; idx += nt) {
         const int r = idx / K, c = idx - r * K;
@@ -208,8 +234,12 @@ __global__ void __launch_bounds__(256) k_left_canon(cplx* __restrict__ mps, int3
       a = K;
       a_old = n;
       __syncthreads();
+      pc[4] += qsp_clock() - tck;
     }
   }
+  (void)red;
+  if (prof && tid == 0)
+    for (int q = 0; q < 8; ++q) prof[(long)blockIdx.x * 8 + q] += pc[q];
 }
 
 // ----------------------------------------------------------------------------------
