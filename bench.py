@@ -49,17 +49,34 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--second-pass", action="store_true")
+    ap.add_argument("--workload", default="random", choices=["random", "heisenberg"],
+                    help="random: SURVEY 8d synthetic MPS; heisenberg: the reference's L=32 ground state "
+                         "(tests/golden/heisenberg_L32.npz) replicated over the batch (cfg 3a: --layers 6 --chi 32)")
     return ap.parse_args()
 
 
 def workload_name(a):
+    if a.workload == "heisenberg":
+        return f"heisenberg_L32_pickle_replicated_layers{a.layers}_compress_maxbond{a.chi}"
     return f"random_mps_L{a.L}_chi{a.chi}_d2_layers{a.layers}_compress_maxbond{a.chi}"
+
+
+def heisenberg_batch(torch, B, chi, dev):
+    """cfg 3a: the Heisenberg L=32 ground state shipped with the reference, replicated B times."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "heisenberg_L32.npz"))
+    m, b = z["mps"].astype(np.complex128), z["bonds"].astype(np.int32)
+    D = max(int(b.max()), chi)
+    pad = np.zeros((m.shape[0], D, 2, D), np.complex128)
+    pad[:, : m.shape[1], :, : m.shape[3]] = m
+    x = torch.from_numpy(pad).to(dev).unsqueeze(0).repeat(B, 1, 1, 1, 1).contiguous()
+    bonds = torch.from_numpy(b).to(dev).unsqueeze(0).repeat(B, 1).contiguous()
+    return x, bonds
 
 
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle (numpy restatement of the reference path; quimb is not installable)
 # --------------------------------------------------------------------------------------
-def cpu_sample(L, chi, layers_sample, n_inst, cores, reps=1, timeout=420):
+def cpu_sample(L, chi, layers_sample, n_inst, cores, reps=1, timeout=420, workload="random"):
     """n_inst instances x layers_sample layers on `cores` single-threaded oracle workers, in a
     separate interpreter (BLAS threads pinned to 1 through the environment) -> list of wall seconds."""
     env = dict(os.environ)
@@ -67,7 +84,7 @@ def cpu_sample(L, chi, layers_sample, n_inst, cores, reps=1, timeout=420):
         env[k] = "1"
     env["CUDA_VISIBLE_DEVICES"] = ""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_bench_worker.py"), str(L), str(chi), str(layers_sample),
-                          str(n_inst), str(cores), str(reps)], env=env, capture_output=True, text=True, timeout=timeout)
+                          str(n_inst), str(cores), str(reps), workload], env=env, capture_output=True, text=True, timeout=timeout)
     if out.returncode != 0:
         raise RuntimeError(out.stderr[-2000:])
     return json.loads(out.stdout.strip().splitlines()[-1])
@@ -87,7 +104,7 @@ def cpu_baseline(a):
     cores = cpu_cores()
     log(f"cpu_baseline: {cores} oracle workers, 1 layer each ...")
     try:
-        wall = cpu_sample(a.L, a.chi, 1, cores, cores)[0]
+        wall = cpu_sample(a.L, a.chi, 1, cores, cores, workload=a.workload)[0]
     except Exception as e:  # noqa: BLE001
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {str(e)[:200]}"}
     v = cores / (wall * a.layers)
@@ -103,7 +120,9 @@ def run_reference(a):
         return
     cores = cpu_cores()
     steps = max(1, min(a.steps, 3))
-    walls = cpu_sample(a.L, a.chi, 1, cores, cores, reps=steps, timeout=900)
+    if a.workload == "heisenberg":
+        a.L = 32
+    walls = cpu_sample(a.L, a.chi, 1, cores, cores, reps=steps, timeout=900, workload=a.workload)
     t = float(np.mean(walls))
     v = cores / (t * a.layers)
     sample = (f"each step = {cores} instances x 1 of {a.layers} layers of {workload_name(a)} on {cores} "
@@ -209,7 +228,11 @@ def main():
     B, L, chi, layers = a.batch, a.L, a.chi, a.layers
 
     # ---- inputs resident in HBM (batch * 32 chi^2 L bytes >> 126 MB L2 at the default shape) ----
-    raw, bonds0 = synth_batch(torch, B, L, chi, dev, 1234 + rank)
+    if a.workload == "heisenberg":
+        raw, bonds0 = heisenberg_batch(torch, B, chi, dev)
+        L = a.L = raw.shape[1]
+    else:
+        raw, bonds0 = synth_batch(torch, B, L, chi, dev, 1234 + rank)
     tgt, tb = raw.clone(), bonds0.clone()
     st = eng.prepare_target(tgt, tb)
     torch.cuda.synchronize()

@@ -16,12 +16,24 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def one(args):
     L, chi, layers, seed = args
+    import numpy as np
+
     from oracle import qsp_oracle as O
 
-    t = O.prepare_target(O.random_mps(L, chi, seed), "lpr")
+    if WORKLOAD == "heisenberg" and L == 32:
+        z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                 "heisenberg_L32.npz"))
+        b, m = z["bonds"], z["mps"]
+        raw = [m[i, : b[i], :, : b[i + 1]].copy() for i in range(len(b) - 1)]
+    else:
+        raw = O.random_mps(L, chi, seed)
+    t = O.prepare_target(raw, "lpr")
     t0 = time.time()
     O.sequential_unitary_circuit(t, layers, do_compression=True, max_bond_dim=chi, completion="lapack")
     return time.time() - t0
+
+
+WORKLOAD = sys.argv[7] if len(sys.argv) > 7 else "random"
 
 
 def main():

@@ -129,9 +129,10 @@ static bool plan_rcompress(int Din, int Dout, const DevInfo& d, RCompressPlan* p
   long budget = ((long)d.max_smem - (long)fixed) / (long)sizeof(cplx);
   long gem = (long)(qsp_gemm_smem_bytes(p->nt) / sizeof(cplx));
   if (budget < gem) return false;
-  long je = need < budget ? need : budget;
   // at least two rows of the longest possible row must fit
   long maxlen = imax((int)r32(2 * Dout), (int)(r32(Din) + r32(cmax)));
+  if (need < 2 * maxlen) need = 2 * maxlen;
+  long je = need < budget ? need : budget;
   if (je < 2 * maxlen) return false;
   p->jac_elems = (int)je;
   p->smem = rcompress_smem_bytes(p->jac_elems, Dout, p->nt);

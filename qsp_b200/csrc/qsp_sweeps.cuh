@@ -59,8 +59,11 @@ __device__ __forceinline__ void qr_make_reflector(cplx* col, int j, int m, int l
   } else {
     const double nrm = sqrt(cabs2(alpha) + xn2);
     bt = alpha.x >= 0.0 ? -nrm : nrm;
-    t = cmake((bt - alpha.x) / bt, -alpha.y / bt);
-    const cplx sc = cdiv(cmake(1.0, 0.0), cmake(alpha.x - bt, alpha.y));
+    const double ibt = 1.0 / bt;
+    t = cmake((bt - alpha.x) * ibt, -alpha.y * ibt);
+    const double dx = alpha.x - bt;                   // |alpha - beta|^2 = dx^2 + alpha.y^2, no cancellation (signs agree)
+    const double id2 = 1.0 / fma(dx, dx, alpha.y * alpha.y);
+    const cplx sc = cmake(dx * id2, -alpha.y * id2);  // 1 / (alpha - beta)
     for (int r = j + 1 + lane; r < m; r += 32) col[r] = cmul(col[r], sc);
   }
   if (lane == 0) {
@@ -71,11 +74,12 @@ __device__ __forceinline__ void qr_make_reflector(cplx* col, int j, int m, int l
 }
 
 // col <- (I - f v v^H) col on rows j..m-1, v held in registers (vr), v_j = 1.
-__device__ __forceinline__ void qr_apply_reflector(const cplx* vr, cplx* colc, int j, int m, int lane, cplx f) {
-  cplx cr[QSP_QR_MAXR];
+template <int MAXR>
+__device__ __forceinline__ void qr_apply_reflector(const cplx (&vr)[MAXR], cplx* colc, int j, int m, int lane, cplx f) {
+  cplx cr[MAXR];
   cplx w = cmake(0.0, 0.0);
 #pragma unroll
-  for (int k = 0; k < QSP_QR_MAXR; ++k) {
+  for (int k = 0; k < MAXR; ++k) {
     const int r = j + lane + 32 * k;
     if (r < m) {
       cr[k] = colc[r];
@@ -88,14 +92,31 @@ __device__ __forceinline__ void qr_apply_reflector(const cplx* vr, cplx* colc, i
   }
   const cplx g = cmul(f, w);
 #pragma unroll
-  for (int k = 0; k < QSP_QR_MAXR; ++k) {
+  for (int k = 0; k < MAXR; ++k) {
     const int r = j + lane + 32 * k;
     if (r < m) colc[r] = csub(cr[k], cmul(g, vr[k]));
   }
 }
 
+template <int MAXR>
+__device__ __noinline__ void cta_householder_qr_t(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
+                                                  long long* pc);
+
 __device__ inline void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
                                           long long* pc) {
+  if (m <= 32)
+    cta_householder_qr_t<1>(S, m, n, ldS, R, ldR, tau, beta, pc);
+  else if (m <= 64)
+    cta_householder_qr_t<2>(S, m, n, ldS, R, ldR, tau, beta, pc);
+  else if (m <= 128)
+    cta_householder_qr_t<4>(S, m, n, ldS, R, ldR, tau, beta, pc);
+  else
+    cta_householder_qr_t<QSP_QR_MAXR>(S, m, n, ldS, R, ldR, tau, beta, pc);
+}
+
+template <int MAXR>
+__device__ __noinline__ void cta_householder_qr_t(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
+                                                  long long* pc) {
   long long tck = qsp_clock();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int K = imin(m, n);
@@ -104,20 +125,34 @@ __device__ inline void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* 
   for (int j = 0; j < K; ++j) {
     const cplx* colj = S + (long)j * ldS;
     const cplx tj = tau[j];
-    cplx vr[QSP_QR_MAXR];
+    cplx vr[MAXR];
 #pragma unroll
-    for (int k = 0; k < QSP_QR_MAXR; ++k) {
+    for (int k = 0; k < MAXR; ++k) {
       const int r = j + lane + 32 * k;
       vr[k] = (r == j) ? cmake(1.0, 0.0) : (r < m ? colj[r] : cmake(0.0, 0.0));
     }
-    // apply H_j^H = I - conj(tau) v v^H to the trailing columns; look-ahead on column j+1
-    for (int c = j + 1 + warp; c < n; c += nw) {
-      cplx* colc = S + (long)c * ldS;
-      if (tj.x != 0.0 || tj.y != 0.0) qr_apply_reflector(vr, colc, j, m, lane, cconj(tj));
-      if (c == j + 1 && j + 1 < K) {
-        __syncwarp();
-        qr_make_reflector(colc, j + 1, m, lane, tau, beta);
+    // apply H_j^H = I - conj(tau) v v^H to the trailing columns.  Warp 0 takes column j+1 and
+    // then builds reflector j+1 (look-ahead, the critical path); the other warps share the rest.
+    const bool nz = (tj.x != 0.0 || tj.y != 0.0);
+    if (nw == 1) {
+      for (int c = j + 1; c < n; ++c) {
+        if (nz) qr_apply_reflector(vr, S + (long)c * ldS, j, m, lane, cconj(tj));
+        if (c == j + 1 && j + 1 < K) {
+          __syncwarp();
+          qr_make_reflector(S + (long)c * ldS, j + 1, m, lane, tau, beta);
+        }
       }
+    } else if (warp == 0) {
+      if (j + 1 < n) {
+        cplx* colc = S + (long)(j + 1) * ldS;
+        if (nz) qr_apply_reflector(vr, colc, j, m, lane, cconj(tj));
+        if (j + 1 < K) {
+          __syncwarp();
+          qr_make_reflector(colc, j + 1, m, lane, tau, beta);
+        }
+      }
+    } else if (nz) {
+      for (int c = j + 2 + (warp - 1); c < n; c += nw - 1) qr_apply_reflector(vr, S + (long)c * ldS, j, m, lane, cconj(tj));
     }
     __syncthreads();
   }
@@ -140,9 +175,9 @@ __device__ inline void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* 
     cplx* colj = S + (long)j * ldS;
     const cplx tj = tau[j];
     if (tj.x != 0.0 || tj.y != 0.0) {
-      cplx vr[QSP_QR_MAXR];
+      cplx vr[MAXR];
 #pragma unroll
-      for (int k = 0; k < QSP_QR_MAXR; ++k) {
+      for (int k = 0; k < MAXR; ++k) {
         const int r = j + lane + 32 * k;
         vr[k] = (r == j) ? cmake(1.0, 0.0) : (r < m ? colj[r] : cmake(0.0, 0.0));
       }

@@ -88,6 +88,34 @@ def layers_to_gates(gs_lst, L):
     return G, kind
 
 
+def edge_cases():
+    """inputs at the edges of what the reference accepts: (raw mps, layers, max_bond, padded bond)"""
+    from oracle import qsp_oracle as O
+
+    rng = np.random.default_rng(0)
+    prod = [rng.standard_normal((1, 2, 1)) + 1j * rng.standard_normal((1, 2, 1)) for _ in range(5)]
+    padded = [np.zeros((1 if i == 0 else 3, 2, 1 if i == 4 else 3), complex) for i in range(5)]
+    for i in range(5):
+        padded[i][0, :, 0] = prod[i][0, :, 0]
+    L = 6
+    ghz = []
+    for i in range(L):
+        a = np.zeros((1 if i == 0 else 2, 2, 1 if i == L - 1 else 2), complex)
+        for s in range(2):
+            a[0 if i == 0 else s, s, 0 if i == L - 1 else s] = 1
+        ghz.append(a)
+    return {
+        "product_state": (prod, 2, 0, 4),
+        "rank_deficient_padding": (padded, 2, 0, 8),
+        "ghz_degenerate_schmidt": (ghz, 2, 0, 8),
+        "single_site": ([rng.standard_normal((1, 2, 1)) + 0j], 1, 0, 2),
+        "two_sites": (O.random_mps(2, 2, 1), 2, 0, 2),
+        "three_sites_compressed": (O.random_mps(3, 2, 2), 2, 2, 2),
+        "real_input": (O.random_mps(6, 4, 3, dtype=np.float64), 2, 4, 4),
+    }
+
+
+
 class HostDriver:
     """Unit-level calls on numpy buffers (emulated build)."""
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import proto_fused as P
-from helpers import HostDriver, gates_to_layers, layers_to_gates, pack_batch, unpack_batch
+from helpers import HostDriver, edge_cases, gates_to_layers, layers_to_gates, pack_batch, unpack_batch
 from oracle import qsp_oracle as O
 
 
@@ -197,3 +197,22 @@ def test_status_bits_and_error_codes(drv):
     # unsupported size is reported before anything is launched
     assert drv.lib.qsp_seq_prepare_workspace_bytes(1, 10, 512, 2, 512, 0) == 0
     assert drv.lib._qsp_left_canonize(None, None, 1, 4, 4, None, None) == 1
+
+
+@pytest.mark.parametrize("name", list(edge_cases()))
+def test_edge_cases(drv, name):
+    """empty-ish and ragged inputs the reference accepts: product states (every bond 1, all
+    one-qubit gates), zero-padded rank-deficient tensors, degenerate Schmidt values, L = 1, 2, 3."""
+    raw, layers, mb, D = edge_cases()[name]
+    t = _prepared(raw)
+    a, b = pack_batch([t], D)
+    r = drv.seq_prepare(a, b, layers, max_bond=mb)
+    assert r["status"][0] == 0
+    dev_layers = [gates_to_layers(r["G"][j, 0], r["kind"][j, 0]) for j in range(layers)]
+    kw = dict(do_compression=mb > 0, max_bond_dim=mb or None)
+    tf = O.sequential_unitary_circuit(t, layers, unitaries_override=dev_layers, **kw)
+    ev = [i for i in range(layers) if i % 4 == 0 or i == layers - 1]
+    assert np.abs(np.array(tf["disentangled_mps_overlaps"]) - r["dis"][:, 0]).max() < 1e-12
+    assert np.abs(np.array(tf["overlaps"]) - r["overlaps"][ev, 0]).max() < 1e-12
+    sc = O.sequential_unitary_circuit(t, layers, completion="canonical", **kw)
+    assert [O.unitaries_specs(l) for l in sc["unitaries"]] == [O.unitaries_specs(l) for l in dev_layers]

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import gates_to_layers, pack_batch, unpack_batch
+from helpers import edge_cases, gates_to_layers, pack_batch, unpack_batch
 from oracle import qsp_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -207,6 +207,20 @@ def test_pipeline_chi64(drv):
     """headline bond dimension on a short chain (the oracle needs seconds per instance)."""
     tg = [_prepared(O.random_mps(16, 64, 90 + s)) for s in range(2)]
     _check_pipeline(drv, tg, 2, 64, 64)
+
+
+@pytest.mark.parametrize("name", list(edge_cases()))
+def test_pipeline_edge_cases(drv, name):
+    """product states, rank-deficient padding, degenerate Schmidt values, L = 1, 2, 3, real input."""
+    raw, layers, mb, D = edge_cases()[name]
+    _check_pipeline(drv, [_prepared(raw)], layers, mb, D, same_convention=(name != "ghz_degenerate_schmidt"),
+                    check_svals=(name != "ghz_degenerate_schmidt"))
+
+
+def test_pipeline_six_layers_heisenberg(drv):
+    """BASELINE configs[2] shape: Heisenberg L=32 ground state, 6 layers, max_bond_dim=32 (teacher-forced)."""
+    z, mps = _load_gold("heisenberg_L32")
+    _check_pipeline(drv, [_prepared(mps)], 6, 32, 32, same_convention=False)
 
 
 def test_golden_heisenberg_layer1(drv):
