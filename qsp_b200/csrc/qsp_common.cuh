@@ -24,9 +24,11 @@ typedef cudaStream_t qsp_stream_t;
 #ifdef QSP_EMU
 inline long long qsp_clock() { return 0; }
 inline double qsp_rsqrt(double x) { return 1.0 / sqrt(x); }
+inline void qsp_spin_hint() { emu_spin_yield(); }
 #else
 __device__ __forceinline__ long long qsp_clock() { return clock64(); }
 __device__ __forceinline__ double qsp_rsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ void qsp_spin_hint() {}
 #endif
 
 #define QSP_FULL_MASK 0xffffffffu

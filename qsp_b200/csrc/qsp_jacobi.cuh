@@ -181,6 +181,7 @@ __device__ int g_jvar = 0;
 #else
 #define QSP_JV() (0)
 #endif
+#define QSP_JCH 2    // columns of the shared row fetched per batch in the streaming (non-HOLD) path
 #define QSP_JPAD 32
 // A sweep whose largest rotated |g|/sqrt(alpha beta) is <= QSP_JAC_QUAD leaves off-diagonals of
 // order n * QSP_JAC_QUAD^2 ~ 1e-16 (quadratic convergence): no verification sweep is needed.
@@ -264,19 +265,46 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
             if (j < jlen) x[HOLD ? j : 0] = xs[j * tpp];
         }
         double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
+        if (HOLD) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-          if (j < jdot && !(jv & 1)) {
-            const cplx y = R[q][j];
-            const cplx xv = HOLD ? x[HOLD ? j : 0] : xs[j * tpp];
-            al = fma(xv.x, xv.x, al);
-            al = fma(xv.y, xv.y, al);
-            be = fma(y.x, y.x, be);
-            be = fma(y.y, y.y, be);
-            gx = fma(xv.x, y.x, gx);
-            gx = fma(xv.y, y.y, gx);
-            gy = fma(xv.y, y.x, gy);
-            gy = fma(-xv.x, y.y, gy);
+          for (int j = 0; j < CPL; ++j) {
+            if (j < jdot && !(jv & 1)) {
+              const cplx y = R[q][j];
+              const cplx xv = x[HOLD ? j : 0];
+              al = fma(xv.x, xv.x, al);
+              al = fma(xv.y, xv.y, al);
+              be = fma(y.x, y.x, be);
+              be = fma(y.y, y.y, be);
+              gx = fma(xv.x, y.x, gx);
+              gx = fma(xv.y, y.y, gx);
+              gy = fma(xv.y, y.x, gy);
+              gy = fma(-xv.x, y.y, gy);
+            }
+          }
+        } else {
+          // the shared row is streamed in chunks of QSP_JCH columns: the loads of a chunk are issued
+          // together (independent registers), then consumed -- one shared-memory latency per chunk
+#pragma unroll
+          for (int j0 = 0; j0 < CPL; j0 += QSP_JCH) {
+            cplx xt[QSP_JCH];
+#pragma unroll
+            for (int u = 0; u < QSP_JCH; ++u)
+              if (j0 + u < jdot && !(jv & 1)) xt[u] = xs[(j0 + u) * tpp];
+#pragma unroll
+            for (int u = 0; u < QSP_JCH; ++u) {
+              if (j0 + u < jdot && !(jv & 1)) {
+                const cplx y = R[q][j0 + u];
+                const cplx xv = xt[u];
+                al = fma(xv.x, xv.x, al);
+                al = fma(xv.y, xv.y, al);
+                be = fma(y.x, y.x, be);
+                be = fma(y.y, y.y, be);
+                gx = fma(xv.x, y.x, gx);
+                gx = fma(xv.y, y.y, gx);
+                gy = fma(xv.y, y.x, gy);
+                gy = fma(-xv.x, y.y, gy);
+              }
+            }
           }
         }
         if (!(jv & 2))
@@ -297,17 +325,24 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
               jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
             if (tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) *flag = 1;
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) {
-              if (j < jlen) {
-                const cplx y = R[q][j];
-                const cplx xv = HOLD ? x[HOLD ? j : 0] : xs[j * tpp];
-                cplx xn, yn;
-                xn.x = fma(cs, xv.x, fma(sy, y.y, -sx * y.x));
-                xn.y = fma(cs, xv.y, -fma(sx, y.y, sy * y.x));
-                yn.x = fma(cs, y.x, fma(sx, xv.x, sy * xv.y));
-                yn.y = fma(cs, y.y, fma(sx, xv.y, -sy * xv.x));
-                xs[j * tpp] = yn;  // the rows trade places
-                R[q][j] = xn;
+            for (int j0 = 0; j0 < CPL; j0 += QSP_JCH) {
+              cplx xt[QSP_JCH];
+#pragma unroll
+              for (int u = 0; u < QSP_JCH; ++u)
+                if (j0 + u < jlen) xt[u] = HOLD ? x[HOLD ? j0 + u : 0] : xs[(j0 + u) * tpp];
+#pragma unroll
+              for (int u = 0; u < QSP_JCH; ++u) {
+                if (j0 + u < jlen) {
+                  const cplx y = R[q][j0 + u];
+                  const cplx xv = xt[u];
+                  cplx xn, yn;
+                  xn.x = fma(cs, xv.x, fma(sy, y.y, -sx * y.x));
+                  xn.y = fma(cs, xv.y, -fma(sx, y.y, sy * y.x));
+                  yn.x = fma(cs, y.x, fma(sx, xv.x, sy * xv.y));
+                  yn.y = fma(cs, y.y, fma(sx, xv.y, -sy * xv.x));
+                  xs[(j0 + u) * tpp] = yn;  // the rows trade places
+                  R[q][j0 + u] = xn;
+                }
               }
             }
           } else {

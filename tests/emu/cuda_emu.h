@@ -150,6 +150,8 @@ inline int __shfl_sync(unsigned m, int v, int src, int width = 32) {
 inline int __shfl_xor_sync(unsigned m, int v, int mask, int width = 32) {
   return (int)__shfl_xor_sync(m, (double)v, mask, width);
 }
+inline void __threadfence_block() {}
+inline void emu_spin_yield() { emu::yield(); }
 inline char* emu_dynamic_smem() {
   uintptr_t p = (uintptr_t)emu::g_blk->smem.data();
   return (char*)((p + 15) & ~(uintptr_t)15);
