@@ -133,6 +133,8 @@ void qsp_set_profile_buffer(void* buf);
 
 /* Development aid: Jacobi micro-benchmark, W[B][nrows][ldw] orthogonalised in place (ldw a
  * multiple of 32), nt threads per CTA. */
+int qsp_jacobi_bench_fat(qsp_c128* W, int nrows, int ldw, int B, int* sweeps, int* ok, void* stream);
+int qsp_smem_probe(double* out, int blocks, int iters, int mode, void* stream); /* shared-memory bandwidth probe */
 void qsp_jacobi_variant(int bits); /* timing experiments: disables parts of the Jacobi round (results invalid) */
 int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int nt, int* sweeps, int* ok, void* stream);
 

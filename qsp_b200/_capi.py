@@ -33,6 +33,8 @@ _SIGNATURES = {
     "qsp_prepare_target": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _sz, _p]),
     "qsp_seq_prepare_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "qsp_set_profile_buffer": (None, [_p]),
+    "qsp_jacobi_bench_fat": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "qsp_smem_probe": (_i, [_p, _i, _i, _i, _p]),
     "qsp_jacobi_variant": (None, [_i]),
     "qsp_jacobi_bench": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "qsp_dfma_probe": (_i, [_p, _i, _i, _i, _p]),

@@ -320,6 +320,74 @@ __global__ void __launch_bounds__(NTMAX) k_jacobi_bench(cplx* W, int nrows, int 
     __syncthreads();
   }
 }
+// Experiment: "fat thread" geometry -- 256 threads, teams of 4 lanes, 32 columns per lane (row half
+// in 128 registers), so that latency is hidden by instruction-level parallelism instead of warps.
+__global__ void __launch_bounds__(256) k_jacobi_bench_fat(cplx* W, int nrows, int ldw, int B, int* sweeps, int* ok) {
+  char* sm = QSP_SMEM_BASE();
+  const int cap_elems = ((nrows + 1) / 2) * ldw;
+  double* red = (double*)(sm + (size_t)cap_elems * sizeof(cplx));
+  const int tpp = 4;
+  for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    int ns = 0;
+    const double tol = 4e-16 * sqrt((double)ldw);
+    bool c = jacobi_rows_oe<32, 1, false>(W + (long)inst * nrows * ldw, nrows, ldw / tpp, ldw / tpp, 0, tpp, tol * tol, 60,
+                                          (int)((char*)red - sm), &ns);
+    if (threadIdx.x == 0) {
+      sweeps[inst] = ns;
+      ok[inst] = c ? 1 : 0;
+    }
+    __syncthreads();
+  }
+}
+extern "C" int qsp_jacobi_bench_fat(qsp_c128* W, int nrows, int ldw, int B, int* sweeps, int* ok, void* stream) {
+  DevInfo d = dev_info();
+  if (nrows / 2 > 64 || ldw != 128) return QSP_ERR_ARG;
+  size_t smem = (size_t)((nrows + 1) / 2) * ldw * sizeof(cplx) + 64 * sizeof(double) + 64;
+  int grid = B < d.sms ? B : d.sms;
+  QSP_PREP_KERNEL(k_jacobi_bench_fat, smem);
+  QSP_LAUNCH(k_jacobi_bench_fat, grid, 256, smem, (qsp_stream_t)stream, (cplx*)W, nrows, ldw, B, sweeps, ok);
+  ++g_launches;
+  return check_launch();
+}
+// Shared-memory bandwidth probe with the Jacobi access pattern (teams of tpp lanes, 16-byte
+// elements, 16 per lane, rows of 2 KB): mode 0 = load only, 1 = store only, 2 = load + store.
+__global__ void __launch_bounds__(512) k_smem_probe(double* out, int iters, int mode) {
+  cplx* S = (cplx*)QSP_SMEM_BASE();
+  const int tid = threadIdx.x, tpp = 8, team = tid / tpp, tl = tid % tpp;
+  for (int i = tid; i < 64 * 128; i += blockDim.x) S[i] = cmake(i, -i);
+  __syncthreads();
+  cplx R[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) R[j] = cmake(j, tid);
+  cplx acc = cmake(0, 0);
+  for (int it = 0; it < iters; ++it) {
+    cplx* xs = S + ((team + (it & 1)) & 63) * 128 + tl;
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc = cadd(acc, xs[j * tpp]);
+    } else if (mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) xs[j * tpp] = R[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        cplx x = xs[j * tpp];
+        xs[j * tpp] = R[j];
+        R[j] = x;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc = cadd(acc, R[j]);
+  if (acc.x == 1.2345e300) out[0] = acc.y;
+}
+extern "C" int qsp_smem_probe(double* out, int blocks, int iters, int mode, void* stream) {
+  size_t smem = 64 * 128 * sizeof(cplx);
+  QSP_PREP_KERNEL(k_smem_probe, smem);
+  QSP_LAUNCH(k_smem_probe, blocks, 512, smem, (qsp_stream_t)stream, out, iters, mode);
+  ++g_launches;
+  return check_launch();
+}
 extern "C" void qsp_jacobi_variant(int v) {
 #ifdef QSP_JACOBI_ABLATION
   cudaMemcpyToSymbol(g_jvar, &v, sizeof(int));

@@ -25,10 +25,15 @@ typedef cudaStream_t qsp_stream_t;
 inline long long qsp_clock() { return 0; }
 inline double qsp_rsqrt(double x) { return 1.0 / sqrt(x); }
 inline void qsp_spin_hint() { emu_spin_yield(); }
+inline void qsp_named_barrier(int id, int count) { emu_named_barrier(id, count); }
 #else
 __device__ __forceinline__ long long qsp_clock() { return clock64(); }
 __device__ __forceinline__ double qsp_rsqrt(double x) { return rsqrt(x); }
 __device__ __forceinline__ void qsp_spin_hint() {}
+// bar.sync on one of the 15 named hardware barriers (id 1..15), `count` threads (multiple of 32)
+__device__ __forceinline__ void qsp_named_barrier(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 #endif
 
 #define QSP_FULL_MASK 0xffffffffu

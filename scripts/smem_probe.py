@@ -1,0 +1,15 @@
+import os, sys, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from qsp_b200 import _runtime
+lib = _runtime.lib(); dev = torch.device("cuda:0")
+out = torch.zeros(8, dtype=torch.float64, device=dev)
+s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+iters = 20000
+for mode, name, passes in ((0, "load", 1), (1, "store", 1), (2, "load+store", 2)):
+    for rep in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); lib.qsp_smem_probe(ctypes.c_void_p(out.data_ptr()), 148, iters, mode, s); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    cyc = ms * 1e-3 * 1.965e9 / iters
+    print(f"{name}: {cyc:.0f} cycles per iteration per SM for {passes} x 128 KB -> {passes * 131072 / cyc:.1f} B/clk/SM")

@@ -48,6 +48,7 @@ struct Block {
   ucontext_t sched;
   std::vector<char> smem;
   Group bar;
+  Group named[16];
   std::vector<Group> warp_bar;
   std::vector<double> xchg;  // 32 doubles per warp
   std::function<void()> body;
@@ -151,6 +152,7 @@ inline int __shfl_xor_sync(unsigned m, int v, int mask, int width = 32) {
   return (int)__shfl_xor_sync(m, (double)v, mask, width);
 }
 inline void __threadfence_block() {}
+inline void emu_named_barrier(int id, int count) { emu::group_sync(emu::g_blk->named[id & 15], (unsigned)count); }
 inline void emu_spin_yield() { emu::yield(); }
 inline char* emu_dynamic_smem() {
   uintptr_t p = (uintptr_t)emu::g_blk->smem.data();
