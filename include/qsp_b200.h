@@ -104,6 +104,16 @@ size_t qsp_prepare_target_workspace_bytes(int B, int L, int D);
 int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, int D, double cutoff, int32_t* status,
                        void* work, size_t work_bytes, void* stream);
 
+/* apply_unitary_layers_on_wfn(unitaries, |0..0>) + right_canonize(normalize) + norm_mps_ovrlap with the
+ * target (core.py:217-221, sequential.py:67-70, tsp.py:130-132): result[b] = <target_b| U_0 ... U_{n-1} |0..0>
+ * for G[n][B][L][4][4], kind[n][B][L].  Every forward layer is applied exactly (bonds double); the
+ * reference's cutoff-only compress('right') after each layer does not change the state and is only run
+ * when the doubled bonds would not fit (more than 8 layers on chains of at most 11 sites). */
+size_t qsp_encoded_overlap_workspace_bytes(int B, int L, int D, int layers);
+int qsp_encoded_overlap(const qsp_c128* G, const int32_t* kind, int n, const qsp_c128* target,
+                        const int32_t* target_bonds, int B, int L, int D, double cutoff, qsp_c128* result,
+                        int32_t* status, void* work, size_t work_bytes, void* stream);
+
 /* The whole layer loop of sequential_unitary_circuit (sequential.py:42-85) for a batch.
  *   target / target_bonds : right-canonical normalised MPS (qsp_prepare_target output), D-padded;
  *                           every bond must stay <= D at every layer start (with

@@ -31,6 +31,8 @@ _SIGNATURES = {
     "qsp_overlap": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p, _p, _sz, _p]),
     "qsp_prepare_target_workspace_bytes": (_sz, [_i, _i, _i]),
     "qsp_prepare_target": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _sz, _p]),
+    "qsp_encoded_overlap_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "qsp_encoded_overlap": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _d, _p, _p, _p, _sz, _p]),
     "qsp_seq_prepare_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "qsp_set_profile_buffer": (None, [_p]),
     "qsp_jacobi_bench_fat": (_i, [_p, _i, _i, _i, _p, _p, _p]),

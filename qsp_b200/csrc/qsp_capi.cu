@@ -154,16 +154,23 @@ extern "C" const char* qsp_last_cuda_error(void) { return g_err; }
 extern "C" void qsp_set_profile_buffer(void* p) { g_prof = (long long*)p; }
 extern "C" long long qsp_launch_count(void) { return g_launches; }
 
-extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* stream) {
+// Dlive: largest bond that can occur in this call (<= D, the padded stride); the launch (threads,
+// shared memory, CTAs per SM) is planned for Dlive, a larger live bond sets QSP_ST_BOND_OVERFLOW.
+static int left_canonize_live(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int Dlive, int32_t* status,
+                              void* stream) {
   if (!mps || !bonds || B <= 0 || L <= 0 || D <= 0) return QSP_ERR_ARG;
+  if (Dlive > D || Dlive <= 0) Dlive = D;
   DevInfo d = dev_info();
   LCanonPlan p;
-  if (!plan_lcanon(D, d, &p)) return QSP_ERR_UNSUPPORTED;
+  if (!plan_lcanon(Dlive, d, &p)) return QSP_ERR_UNSUPPORTED;
   QSP_PREP_KERNEL(k_left_canon, p.smem);
   int grid = grid_for(B, blocks_per_sm((const void*)k_left_canon, p.nt, p.smem), d);
-  QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, D, status, g_prof);
+  QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, Dlive, status, g_prof);
   ++g_launches;
   return check_launch();
+}
+extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* stream) {
+  return left_canonize_live(mps, bonds, B, L, D, D, status, stream);
 }
 
 static int rcompress_grid(int B, const RCompressPlan& p, const DevInfo& d) {
@@ -182,18 +189,20 @@ extern "C" size_t qsp_right_compress_workspace_bytes(int B, int L, int D_in, int
   return align_up((size_t)grid * rcompress_work_elems(D_in, D_out) * sizeof(cplx));
 }
 
-extern "C" int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, int D_in, qsp_c128* out,
-                                  int32_t* bonds_out, int D_out, int B, int L, int max_bond, double cutoff,
-                                  int normalize, double* svals, int nsv, qsp_c128* amp0, int32_t* status, void* work,
-                                  size_t work_bytes, void* stream) {
+static int right_compress_live(const qsp_c128* in, const int32_t* bonds_in, int D_in, qsp_c128* out,
+                               int32_t* bonds_out, int D_out, int DinL, int DoutL, int B, int L, int max_bond,
+                               double cutoff, int normalize, double* svals, int nsv, qsp_c128* amp0, int32_t* status,
+                               void* work, size_t work_bytes, void* stream) {
   if (!in || !bonds_in || !out || !bonds_out || !work || B <= 0 || L <= 0 || D_in <= 0 || D_out <= 0)
     return QSP_ERR_ARG;
+  if (DinL <= 0 || DinL > D_in) DinL = D_in;
+  if (DoutL <= 0 || DoutL > D_out) DoutL = D_out;
   DevInfo d = dev_info();
   RCompressPlan p;
-  if (!plan_rcompress(D_in, D_out, d, &p)) return QSP_ERR_UNSUPPORTED;
+  if (!plan_rcompress(DinL, DoutL, d, &p)) return QSP_ERR_UNSUPPORTED;
   QSP_PREP_KERNEL(k_right_compress, p.smem);
   int grid = rcompress_grid(B, p, d);
-  long stride = rcompress_work_elems(D_in, D_out);
+  long stride = rcompress_work_elems(DinL, DoutL);
   if (work_bytes < (size_t)grid * stride * sizeof(cplx)) return QSP_ERR_WORKSPACE;
   RCompressArgs a;
   a.in = (const cplx*)in;
@@ -202,6 +211,8 @@ extern "C" int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, i
   a.out = (cplx*)out;
   a.bonds_out = bonds_out;
   a.Dout = D_out;
+  a.DinL = DinL;
+  a.DoutL = DoutL;
   a.B = B;
   a.L = L;
   a.max_bond = max_bond;
@@ -220,6 +231,13 @@ extern "C" int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, i
   QSP_LAUNCH(k_right_compress, grid, p.nt, p.smem, (qsp_stream_t)stream, a);
   ++g_launches;
   return check_launch();
+}
+extern "C" int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, int D_in, qsp_c128* out,
+                                  int32_t* bonds_out, int D_out, int B, int L, int max_bond, double cutoff,
+                                  int normalize, double* svals, int nsv, qsp_c128* amp0, int32_t* status, void* work,
+                                  size_t work_bytes, void* stream) {
+  return right_compress_live(in, bonds_in, D_in, out, bonds_out, D_out, D_in, D_out, B, L, max_bond, cutoff, normalize,
+                             svals, nsv, amp0, status, work, work_bytes, stream);
 }
 
 extern "C" int qsp_generate_unitaries(qsp_c128* d2, const int32_t* d2_bonds, int B, int L, qsp_c128* G,
@@ -451,20 +469,99 @@ extern "C" int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, i
 // ------------------------------------------------------------------------------------
 // the layer loop
 // ------------------------------------------------------------------------------------
-struct SeqPlan {
-  int De;   // padded bond of the encoded state: 2^min(layers, L/2)
-  int De2;  // padded bond of its doubled intermediate: 2^min(layers, L/2 + 1)
-  size_t off_psi, off_psib, off_psi2, off_psi2b, off_d2, off_d2b, off_tmp, off_tmpb;
-  size_t off_enc, off_encb, off_enc2, off_enc2b, off_zero, off_zerob, off_scratch;
-  size_t scratch_bytes, total;
+// Encoded state U_0..U_k|0..0> (core.py:217-221).  Every forward layer doubles the bonds exactly
+// (k_expand_forward) and keeps the state right canonical and normalised, so the reference's
+// compress('right') after each layer (core.py:140, cutoff only) changes nothing but the bond
+// sizes.  Mode A (layers <= 8): buffers of 2^layers, no compression at all.  Mode B (more layers,
+// short chains with 2^(L/2+1) <= 64): 64-padded buffers, compress whenever the next doubling would
+// not fit (true rank <= 2^(L/2)).
+struct EncPlan {
+  int De;        // padded bond of both encoded-state buffers
+  bool compress; // mode B
   bool ok;
 };
-static int enc_pad(int L, int layers, int extra) {
-  int cap = L / 2 + extra;
-  int e = layers < cap ? layers : cap;
-  if (e > 20) e = 20;
-  return 1 << e;
+static EncPlan plan_enc(int L, int layers) {
+  EncPlan e;
+  e.ok = true;
+  e.compress = false;
+  if (layers <= 8) {
+    e.De = 1 << layers;
+  } else if (L / 2 + 1 <= 6) {
+    e.De = 64;
+    e.compress = true;
+  } else {
+    e.De = 1;
+    e.ok = false;
+  }
+  return e;
 }
+extern "C" size_t qsp_encoded_overlap_workspace_bytes(int B, int L, int D, int layers) {
+  EncPlan e = plan_enc(L, layers);
+  if (!e.ok) return 0;
+  size_t s = qsp_overlap_workspace_bytes(B, L, e.De, D);
+  if (e.compress) {
+    size_t t = qsp_right_compress_workspace_bytes(B, L, e.De, e.De);
+    if (!t) return 0;
+    s = t > s ? t : s;
+  }
+  return 2 * (mps_bytes(B, L, e.De) + bonds_bytes(B, L)) + s;
+}
+__global__ void k_zero_state(cplx* mps, int32_t* bonds, int B, int L, int D);
+// <target| U_0 ... U_{n-1} |0..0> for G[n][B][L][4][4], kind[n][B][L]  (sequential.py:67-70, tsp.py:130-132)
+extern "C" int qsp_encoded_overlap(const qsp_c128* G, const int32_t* kind, int n, const qsp_c128* target,
+                                   const int32_t* target_bonds, int B, int L, int D, double cutoff, qsp_c128* result,
+                                   int32_t* status, void* work, size_t work_bytes, void* stream) {
+  if (!G || !kind || !target || !target_bonds || !result || !work || n <= 0 || B <= 0 || L <= 0) return QSP_ERR_ARG;
+  EncPlan e = plan_enc(L, n);
+  if (!e.ok) return QSP_ERR_UNSUPPORTED;
+  size_t need = qsp_encoded_overlap_workspace_bytes(B, L, D, n);
+  if (!need) return QSP_ERR_UNSUPPORTED;
+  if (work_bytes < need) return QSP_ERR_WORKSPACE;
+  const int De = e.De;
+  char* w = (char*)work;
+  qsp_c128* ea = (qsp_c128*)w;
+  w += mps_bytes(B, L, De);
+  int32_t* eab = (int32_t*)w;
+  w += bonds_bytes(B, L);
+  qsp_c128* eb = (qsp_c128*)w;
+  w += mps_bytes(B, L, De);
+  int32_t* ebb = (int32_t*)w;
+  w += bonds_bytes(B, L);
+  const size_t sb = work_bytes - (size_t)(w - (char*)work);
+  qsp_stream_t st = (qsp_stream_t)stream;
+  long nl = (long)B * L;
+  QSP_LAUNCH(k_zero_state, (unsigned)((nl + 127) / 128), 128, 0, st, (cplx*)ea, eab, B, L, De);
+  ++g_launches;
+  int rc, cur = 1;
+  const int rank_cap = 1 << imin(L / 2, 20);
+  for (int k = n - 1; k >= 0; --k) {
+    if (2 * cur > De) {  // mode B: bring the bonds back to the true rank before doubling them again
+      if ((rc = left_canonize_live(ea, eab, B, L, De, cur, status, stream))) return rc;
+      if ((rc = right_compress_live(ea, eab, De, eb, ebb, De, cur, imin(cur, rank_cap), B, L, 0, cutoff, 0, nullptr, 0,
+                                    nullptr, status, w, sb, stream)))
+        return rc;
+      qsp_c128* t = ea; ea = eb; eb = t;
+      int32_t* tb = eab; eab = ebb; ebb = tb;
+      cur = imin(cur, rank_cap);
+      if (2 * cur > De) return QSP_ERR_UNSUPPORTED;
+    }
+    const qsp_c128* Gk = G + (size_t)k * B * L * 16;
+    const int32_t* kk = kind + (size_t)k * B * L;
+    if ((rc = qsp_apply_forward_layer(ea, eab, De, Gk, kk, eb, ebb, De, B, L, status, stream))) return rc;
+    qsp_c128* t = ea; ea = eb; eb = t;
+    int32_t* tb = eab; eab = ebb; ebb = tb;
+    cur = 2 * cur;
+  }
+  return qsp_overlap(ea, eab, De, target, target_bonds, D, B, L, result, w, sb, stream);
+}
+
+struct SeqPlan {
+  int De;
+  size_t off_psi, off_psib, off_psi2, off_psi2b, off_d2, off_d2b, off_tmp, off_tmpb;
+  size_t off_enc, off_scratch;
+  size_t enc_bytes, scratch_bytes, total;
+  bool ok;
+};
 static SeqPlan plan_seq(int B, int L, int D, int layers, int max_bond, int flags) {
   (void)max_bond;
   SeqPlan p;
@@ -472,8 +569,7 @@ static SeqPlan plan_seq(int B, int L, int D, int layers, int max_bond, int flags
   p.ok = true;
   const bool enc = !(flags & QSP_FLAG_NO_ENCODED);
   const bool second = (flags & QSP_FLAG_SECOND_PASS) != 0;
-  p.De = enc ? enc_pad(L, layers, 0) : 1;
-  p.De2 = enc ? enc_pad(L, layers, 1) : 1;
+  p.De = 1;
   size_t o = 0;
   p.off_psi = o, o += mps_bytes(B, L, D);
   p.off_psib = o, o += bonds_bytes(B, L);
@@ -501,18 +597,9 @@ static SeqPlan plan_seq(int B, int L, int D, int layers, int max_bond, int flags
     s = t > s ? t : s;
   }
   if (enc) {
-    p.off_enc = o, o += mps_bytes(B, L, p.De);
-    p.off_encb = o, o += bonds_bytes(B, L);
-    // after j layers the encoded state has bonds <= min(2^j, 2^(L/2)), so the doubled
-    // intermediate of any application is <= min(2^layers, 2^(L/2+1)) = De2
-    p.off_enc2 = o, o += mps_bytes(B, L, p.De2);
-    p.off_enc2b = o, o += bonds_bytes(B, L);
-    if (!plan_lcanon(p.De2, d, &lp)) p.ok = false;
-    t = qsp_right_compress_workspace_bytes(B, L, p.De2, p.De);
-    if (!t) p.ok = false;
-    s = t > s ? t : s;
-    t = qsp_overlap_workspace_bytes(B, L, p.De, D);
-    s = t > s ? t : s;
+    p.enc_bytes = qsp_encoded_overlap_workspace_bytes(B, L, D, layers);
+    if (!p.enc_bytes) p.ok = false;
+    p.off_enc = o, o += align_up(p.enc_bytes);
   }
   p.off_scratch = o;
   p.scratch_bytes = s;
@@ -561,13 +648,9 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
   int32_t* d2b = (int32_t*)(w + p.off_d2b);
   qsp_c128* tmp = (qsp_c128*)(w + p.off_tmp);
   int32_t* tmpb = (int32_t*)(w + p.off_tmpb);
-  qsp_c128* enc = (qsp_c128*)(w + p.off_enc);
-  int32_t* encb = (int32_t*)(w + p.off_encb);
-  qsp_c128* enc2 = (qsp_c128*)(w + p.off_enc2);
-  int32_t* enc2b = (int32_t*)(w + p.off_enc2b);
+  void* encw = w + p.off_enc;
   void* scratch = w + p.off_scratch;
   const size_t sb = p.scratch_bytes;
-  const int De = p.De, De2 = p.De2;
   int rc;
 
   dev_copy(psi, target, (size_t)B * L * D * 2 * D * sizeof(cplx), st);
@@ -601,21 +684,8 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
     }
     // sequential.py:67-70: encoded state U_0 .. U_it |0..0> and its overlap with the target
     if (enc_on && (it % overlaps_gap == 0 || it + 1 == layers)) {
-      long n = (long)B * L;
-      QSP_LAUNCH(k_zero_state, (unsigned)((n + 127) / 128), 128, 0, st, (cplx*)enc, encb, B, L, De);
-      ++g_launches;
-      for (int k = it; k >= 0; --k) {
-        const qsp_c128* Gk = G + (size_t)k * B * L * 16;
-        const int32_t* kk = kind + (size_t)k * B * L;
-        if ((rc = qsp_apply_forward_layer(enc, encb, De, Gk, kk, enc2, enc2b, De2, B, L, status, stream)))
-          return rc;
-        if ((rc = qsp_left_canonize(enc2, enc2b, B, L, De2, status, stream))) return rc;
-        if ((rc = qsp_right_compress(enc2, enc2b, De2, enc, encb, De, B, L, 0, cutoff, k == 0 ? 1 : 0, nullptr, 0,
-                                     nullptr, status, scratch, sb, stream)))
-          return rc;
-      }
-      if ((rc = qsp_overlap(enc, encb, De, target, target_bonds, D, B, L, overlaps + (size_t)it * B, scratch, sb,
-                            stream)))
+      if ((rc = qsp_encoded_overlap(G, kind, it + 1, target, target_bonds, B, L, D, cutoff, overlaps + (size_t)it * B,
+                                    status, encw, p.enc_bytes, stream)))
         return rc;
     }
   }

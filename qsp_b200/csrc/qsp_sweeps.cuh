@@ -287,8 +287,9 @@ struct RCompressArgs {
   cplx* out;                // [B][L][Dout][2][Dout]
   int32_t* bonds_out;       // [B][L+1]
   int Dout;
+  int DinL, DoutL;          // largest LIVE bonds the launch was planned for (<= Din, Dout): scratch / shared sizing
   int B, L;
-  int max_bond;             // 0 = unlimited (up to Dout)
+  int max_bond;             // 0 = unlimited (up to DoutL)
   double cutoff;            // relative (quimb cutoff_mode='rel'), no renormalisation
   int normalize;            // divide site 0 by its norm at the end
   double* svals;            // [B][L-1][nsv] largest singular values per bond (bond i between i-1,i at row i-1), or null
@@ -322,25 +323,26 @@ __host__ __device__ inline size_t rcompress_smem_bytes(int jac_elems, int Dout, 
 __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
   char* sm = QSP_SMEM_BASE();
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int Din = P.Din, Dout = P.Dout, L = P.L;
+  const int Din = P.Din, Dout = P.Dout, L = P.L;  // padded strides of the in / out buffers
+  const int DinL = P.DinL, DoutL = P.DoutL;       // live bounds: scratch and shared-memory sizing
   size_t jac_bytes = (size_t)P.cap_rows_elems * sizeof(cplx);
   size_t gem_bytes = qsp_gemm_smem_bytes(nt);
   size_t big = jac_bytes > gem_bytes ? jac_bytes : gem_bytes;
   cplx* Wsm = (cplx*)sm;
   cplx* tiles = (cplx*)sm;  // aliased: GEMMs and Jacobi never overlap in time
   double* norms = (double*)(sm + big);
-  int* perm = (int*)(norms + 2 * Dout);
-  double* red = (double*)(perm + 2 * Dout);
+  int* perm = (int*)(norms + 2 * DoutL);
+  double* red = (double*)(perm + 2 * DoutL);
   red = (double*)(((uintptr_t)red + 7) & ~(uintptr_t)7);
 
   cplx* Mg = P.work + (long)blockIdx.x * P.work_stride;
-  cplx* Wg = Mg + (long)Din * 2 * Dout;
-  cplx* Vg = Wg + (long)2 * Dout * (Din + 2 * Dout + 64);
-  cplx* Cg = Vg + (long)Dout * 2 * Dout;
-  cplx* fg = Cg + (long)Din * Dout;  // two ping-pong vectors for the <0..0| amplitude
+  cplx* Wg = Mg + (long)DinL * 2 * DoutL;
+  cplx* Vg = Wg + (long)2 * DoutL * (DinL + 2 * DoutL + 64);
+  cplx* Cg = Vg + (long)DoutL * 2 * DoutL;
+  cplx* fg = Cg + (long)DinL * DoutL;  // two ping-pong vectors for the <0..0| amplitude
 
   const long sin = (long)Din * 2 * Din, sout = (long)Dout * 2 * Dout;
-  const int kmax = (P.max_bond > 0) ? imin(P.max_bond, Dout) : Dout;
+  const int kmax = (P.max_bond > 0) ? imin(P.max_bond, DoutL) : DoutL;
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tck = 0;
 #define QSP_TICK() (tck = qsp_clock())
@@ -354,8 +356,8 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
     int st = 0;
     bool bad = false;
     for (int i = 0; i <= L; ++i)
-      if (bi[i] > Din || bi[i] < 1) bad = true;
-    if (bi[L] > Dout || bi[0] > Dout) bad = true;
+      if (bi[i] > DinL || bi[i] < 1) bad = true;
+    if (bi[L] > DoutL || bi[0] > DoutL) bad = true;
     if (bad) {
       if (tid == 0 && P.status) P.status[inst] |= QSP_ST_BOND_OVERFLOW;
       continue;
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         }
         __syncthreads();
       } else {
-        cta_zgemm(2 * b, rp, ro, Ai, Din, 1, false, Cg, Dout, 1, false, Mg, rp, 1, false, tiles);
+        cta_zgemm(2 * b, rp, ro, Ai, Din, 1, false, Cg, DoutL, 1, false, Mg, rp, 1, false, tiles);
       }
       if (i == 0) {
         // orthogonality centre: site 0 <- M (b x 2 x rp), optional normalisation
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
           __syncthreads();
           if (tid == 0) {
             cplx acc = cmake(0.0, 0.0);
-            const cplx* f = fg + fcur * Dout;
+            const cplx* f = fg + fcur * DoutL;
             for (int k = 0; k < rp; ++k) cfma(acc, Mg[k], f[k]);
             const double nn = sqrt(n2);
             P.amp0[inst] = (nn > 0.0) ? cscale(acc, 1.0 / nn) : cmake(0.0, 0.0);
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       for (int q = 0; q < nrows; ++q)
         if (norms[perm[q]] > P.cutoff * smax) ++k;  // monotone: counts the leading run
       if (k > kmax) {
-        if (P.max_bond <= 0 || P.max_bond > Dout) st |= QSP_ST_BOND_OVERFLOW;  // cutoff alone did not fit the buffer
+        if (P.max_bond <= 0 || P.max_bond > DoutL) st |= QSP_ST_BOND_OVERFLOW;  // cutoff alone did not fit the buffer
         k = kmax;
       }
       k = imax(k, 1);
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         }
         for (int idx = tid; idx < b * k; idx += nt) {
           const int x = idx / k, q = idx - x * k;
-          Cg[(long)x * Dout + q] = Wg[(long)perm[q] * len + x];
+          Cg[(long)x * DoutL + q] = Wg[(long)perm[q] * len + x];
         }
         __syncthreads();
       } else {
@@ -515,13 +517,13 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         }
         __syncthreads();
         // U s = M Vh^H
-        cta_zgemm(b, k, c, Mg, c, 1, false, Vg, 1, c, true, Cg, Dout, 1, false, tiles);
+        cta_zgemm(b, k, c, Mg, c, 1, false, Vg, 1, c, true, Cg, DoutL, 1, false, tiles);
       }
       QSP_TOCK(4);
       // ---- <0...0| amplitude: f_new[q] = sum_kk Vh[q,(0,kk)] f[kk] ---------------------------
       if (P.amp0) {
-        const cplx* f = fg + fcur * Dout;
-        cplx* fn = fg + (1 - fcur) * Dout;
+        const cplx* f = fg + fcur * DoutL;
+        cplx* fn = fg + (1 - fcur) * DoutL;
         for (int q = tid; q < k; q += nt) {
           cplx acc = cmake(0.0, 0.0);
           for (int kk = 0; kk < rp; ++kk) cfma(acc, Vg[(long)q * c + kk], f[kk]);

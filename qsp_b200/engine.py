@@ -157,28 +157,14 @@ class Engine:
         right_canonize(normalize) + norm_mps_ovrlap, tsp.py:130-132)."""
         n, B, L = G.shape[0], G.shape[1], G.shape[2]
         D = target.shape[2]
-        De, De2 = 2 ** min(n, L // 2), 2 ** min(n, L // 2 + 1)
         dev = self.device
-        enc = torch.zeros((B, L, De, 2, De), dtype=torch.complex128, device=dev)
-        enc[:, :, 0, 0, 0] = 1.0
-        encb = torch.ones((B, L + 1), dtype=torch.int32, device=dev)
-        # after j layers the bonds are <= min(2^j, 2^(L/2)): the doubled intermediate is <= De2
-        enc2 = torch.empty((B, L, De2, 2, De2), dtype=torch.complex128, device=dev)
-        enc2b = torch.empty((B, L + 1), dtype=torch.int32, device=dev)
+        G, kind = G.contiguous(), kind.contiguous()
         status = torch.zeros(B, dtype=torch.int32, device=dev)
-        nb = max(self.lib.qsp_right_compress_workspace_bytes(B, L, De2, De),
-                 self.lib.qsp_overlap_workspace_bytes(B, L, De, D))
-        if nb == 0:
-            raise QspError("encoded state too large for this build (QSP_ERR_UNSUPPORTED)")
-        work = self._workspace(nb)
-        s = _runtime.current_stream_ptr()
-        for k in range(n - 1, -1, -1):
-            Gk, kk = G[k].contiguous(), kind[k].contiguous()
-            self.lib.qsp_apply_forward_layer(_p(enc), _p(encb), De, _p(Gk), _p(kk), _p(enc2), _p(enc2b), De2, B, L,
-                                             _p(status), s)
-            self.lib.qsp_left_canonize(_p(enc2), _p(enc2b), B, L, De2, _p(status), s)
-            self.lib.qsp_right_compress(_p(enc2), _p(enc2b), De2, _p(enc), _p(encb), De, B, L, 0, cutoff,
-                                        1 if k == 0 else 0, None, 0, None, _p(status), _p(work), nb, s)
         res = torch.empty(B, dtype=torch.complex128, device=dev)
-        self.lib.qsp_overlap(_p(enc), _p(encb), De, _p(target), _p(bonds), D, B, L, _p(res), _p(work), nb, s)
+        nb = self.lib.qsp_encoded_overlap_workspace_bytes(B, L, D, n)
+        if nb == 0:
+            raise QspError(f"encoded state of {n} layers on L={L} not supported by this build (QSP_ERR_UNSUPPORTED)")
+        work = self._workspace(nb)
+        self.lib.qsp_encoded_overlap(_p(G), _p(kind), n, _p(target), _p(bonds), B, L, D, cutoff, _p(res), _p(status),
+                                     _p(work), nb, _runtime.current_stream_ptr())
         return res, status

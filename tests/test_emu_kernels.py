@@ -157,7 +157,8 @@ def test_prepare_target(drv):
         assert abs(O.inner(g, ref) - 1.0) < 1e-13
 
 
-@pytest.mark.parametrize("case", ["compressed", "readme_nocomp", "second_pass", "more_layers_than_half_chain"])
+@pytest.mark.parametrize("case", ["compressed", "readme_nocomp", "second_pass", "more_layers_than_half_chain",
+                                  "ten_layers_short_chain"])
 def test_layer_loop(drv, case):
     if case == "readme_nocomp":
         tg = [_prepared(O.to_lpr(O.readme_mps(6, 2, s), "lrp")) for s in range(2)]
@@ -165,6 +166,9 @@ def test_layer_loop(drv, case):
     elif case == "more_layers_than_half_chain":  # encoded state saturates at 2^(L/2)
         tg = [_prepared(O.random_mps(4, 4, 40 + s)) for s in range(1)]
         layers, mb, D, flags = 4, 4, 4, 0
+    elif case == "ten_layers_short_chain":  # > 8 layers: the encoded state is compressed between layers
+        tg = [_prepared(O.random_mps(4, 4, 5))]
+        layers, mb, D, flags = 10, 4, 4, 0
     else:
         tg = [_prepared(O.random_mps(6, 4, 30 + s)) for s in range(2)]
         layers, mb, D, flags = 2, 4, 4, (1 if case == "second_pass" else 0)
