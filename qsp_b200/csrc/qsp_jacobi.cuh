@@ -324,24 +324,41 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int j
             } else
               jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
             if (tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) *flag = 1;
+            if (HOLD) {
 #pragma unroll
-            for (int j0 = 0; j0 < CPL; j0 += QSP_JCH) {
-              cplx xt[QSP_JCH];
-#pragma unroll
-              for (int u = 0; u < QSP_JCH; ++u)
-                if (j0 + u < jlen) xt[u] = HOLD ? x[HOLD ? j0 + u : 0] : xs[(j0 + u) * tpp];
-#pragma unroll
-              for (int u = 0; u < QSP_JCH; ++u) {
-                if (j0 + u < jlen) {
-                  const cplx y = R[q][j0 + u];
-                  const cplx xv = xt[u];
+              for (int j = 0; j < CPL; ++j) {
+                if (j < jlen) {
+                  const cplx y = R[q][j];
+                  const cplx xv = x[HOLD ? j : 0];
                   cplx xn, yn;
                   xn.x = fma(cs, xv.x, fma(sy, y.y, -sx * y.x));
                   xn.y = fma(cs, xv.y, -fma(sx, y.y, sy * y.x));
                   yn.x = fma(cs, y.x, fma(sx, xv.x, sy * xv.y));
                   yn.y = fma(cs, y.y, fma(sx, xv.y, -sy * xv.x));
-                  xs[(j0 + u) * tpp] = yn;  // the rows trade places
-                  R[q][j0 + u] = xn;
+                  xs[j * tpp] = yn;  // the rows trade places
+                  R[q][j] = xn;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j0 = 0; j0 < CPL; j0 += QSP_JCH) {
+                cplx xt[QSP_JCH];
+#pragma unroll
+                for (int u = 0; u < QSP_JCH; ++u)
+                  if (j0 + u < jlen) xt[u] = xs[(j0 + u) * tpp];
+#pragma unroll
+                for (int u = 0; u < QSP_JCH; ++u) {
+                  if (j0 + u < jlen) {
+                    const cplx y = R[q][j0 + u];
+                    const cplx xv = xt[u];
+                    cplx xn, yn;
+                    xn.x = fma(cs, xv.x, fma(sy, y.y, -sx * y.x));
+                    xn.y = fma(cs, xv.y, -fma(sx, y.y, sy * y.x));
+                    yn.x = fma(cs, y.x, fma(sx, xv.x, sy * xv.y));
+                    yn.y = fma(cs, y.y, fma(sx, xv.y, -sy * xv.x));
+                    xs[(j0 + u) * tpp] = yn;  // the rows trade places
+                    R[q][j0 + u] = xn;
+                  }
                 }
               }
             }
