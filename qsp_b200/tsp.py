@@ -98,8 +98,9 @@ class BatchedMPSPreparation:
         self.seq_data = None
 
     def sequential_unitary_circuit(self, num_seq_layers, do_compression=False, max_bond_dim=None, overlaps_gap=4,
-                                   second_pass=False, chunk=None):
-        """Returns (overlaps[B] complex128 tensor on the device, SeqResult)."""
+                                   second_pass=False, chunk=None, check=False):
+        """Returns (overlaps[B] complex128 tensor on the device, SeqResult).  check=True synchronises
+        and raises if any instance reported a QSP_ST_* status bit (res.status keeps them either way)."""
         if do_compression is True and max_bond_dim is None:
             raise ValueError("since do_compression is True, max_bond_dim>0 should be specified")
         mb = int(max_bond_dim) if do_compression else 0
@@ -113,6 +114,11 @@ class BatchedMPSPreparation:
         res = self.engine.seq_prepare(tgt, self.bonds, num_seq_layers, max_bond=mb, overlaps_gap=overlaps_gap,
                                       second_pass=second_pass, chunk=chunk)
         self.seq_data = res
+        if check:
+            bad = torch.nonzero(res.status).flatten()
+            if bad.numel():
+                raise RuntimeError(f"{bad.numel()} of {self.B} instances failed, first: instance {int(bad[0])} "
+                                   f"status {int(res.status[bad[0]]):#x} (QSP_ST_* in include/qsp_b200.h)")
         return res.overlaps[num_seq_layers - 1], res
 
     def unitaries(self, b):
