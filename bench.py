@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--L", type=int, default=100)
     ap.add_argument("--chi", type=int, default=64)
     ap.add_argument("--layers", type=int, default=4)
-    ap.add_argument("--batch", type=int, default=296, help="instances per GPU per step")
+    ap.add_argument("--batch", type=int, default=592, help="instances per GPU per step (4 per SM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--second-pass", action="store_true")

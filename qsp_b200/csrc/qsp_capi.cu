@@ -50,6 +50,7 @@ static void dev_fill_nan(qsp_c128* p, long n, qsp_stream_t) {
   for (long i = 0; i < n; ++i) p[i].re = p[i].im = NAN;
 }
 static void dev_copy(void* dst, const void* src, size_t bytes, qsp_stream_t) { memcpy(dst, src, bytes); }
+static void dev_zero(void* dst, size_t bytes, qsp_stream_t) { memset(dst, 0, bytes); }
 #else
 #define QSP_PREP_KERNEL(kernel, smem) \
   cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))
@@ -78,6 +79,7 @@ static void dev_fill_nan(qsp_c128* p, long n, qsp_stream_t s) {
 static void dev_copy(void* dst, const void* src, size_t bytes, qsp_stream_t s) {
   cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
 }
+static void dev_zero(void* dst, size_t bytes, qsp_stream_t s) { cudaMemsetAsync(dst, 0, bytes, s); }
 #endif
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -186,7 +188,7 @@ extern "C" size_t qsp_right_compress_workspace_bytes(int B, int L, int D_in, int
   QSP_PREP_KERNEL(k_right_compress, p.smem);
 #endif
   int grid = rcompress_grid(B, p, d);
-  return align_up((size_t)grid * rcompress_work_elems(D_in, D_out) * sizeof(cplx));
+  return align_up(256 + (size_t)grid * rcompress_work_elems(D_in, D_out) * sizeof(cplx));
 }
 
 static int right_compress_live(const qsp_c128* in, const int32_t* bonds_in, int D_in, qsp_c128* out,
@@ -203,7 +205,8 @@ static int right_compress_live(const qsp_c128* in, const int32_t* bonds_in, int 
   QSP_PREP_KERNEL(k_right_compress, p.smem);
   int grid = rcompress_grid(B, p, d);
   long stride = rcompress_work_elems(DinL, DoutL);
-  if (work_bytes < (size_t)grid * stride * sizeof(cplx)) return QSP_ERR_WORKSPACE;
+  if (work_bytes < 256 + (size_t)grid * stride * sizeof(cplx)) return QSP_ERR_WORKSPACE;
+  dev_zero(work, 256, (qsp_stream_t)stream);  // instance queue head
   RCompressArgs a;
   a.in = (const cplx*)in;
   a.bonds_in = bonds_in;
@@ -222,8 +225,9 @@ static int right_compress_live(const qsp_c128* in, const int32_t* bonds_in, int 
   a.nsv = nsv;
   a.amp0 = (cplx*)amp0;
   a.status = status;
-  a.work = (cplx*)work;
+  a.work = (cplx*)((char*)work + 256);
   a.work_stride = stride;
+  a.queue = (int*)work;
   a.cap_rows_elems = p.jac_elems;
   a.tpp = p.tpp;
   a.max_sweeps = 60;

@@ -222,9 +222,15 @@ __device__ __forceinline__ void jacobi_rotation(double al, double be, double gx,
   sy = cw * gy;
 }
 
-template <int CPL, int NP, bool HOLD>
-__device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot, int jlen, int s_off, int tpp, double tol2,
+// TPPC > 0 fixes the team width at compile time and FULL asserts jdot == jlen == CPL (no column
+// predicates): the square power-of-two cases of the layer loop get immediate shared-memory offsets
+// and noticeably lower register pressure.
+template <int CPL, int NP, bool HOLD, int TPPC = 0, bool FULL = false>
+__device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int jlen_, int s_off, int tpp_, double tol2,
                                             int max_sweeps, int red_off, int* sweeps_out) {
+  const int tpp = TPPC > 0 ? TPPC : tpp_;
+  const int jlen = FULL ? CPL : jlen_;
+  const int jdot = FULL ? CPL : jdot_;
   cplx* S = (cplx*)(QSP_SMEM_BASE() + s_off);
   double* red = (double*)(QSP_SMEM_BASE() + red_off);
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -427,6 +433,13 @@ __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, 
     const int s_off = (int)((char*)Wsm - QSP_SMEM_BASE()), r_off = (int)((char*)red - QSP_SMEM_BASE());
 #define QSP_OE(C, N, H) \
   jacobi_rows_oe<C, N, H>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
+#define QSP_OEF(C, H) \
+  jacobi_rows_oe<C, 1, H, 8, true>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
+    if (np == 1 && tpp == 8 && jdot == jlen) {  // square power-of-two problems of the layer loop
+      if (jlen == 16) return QSP_OEF(16, false);
+      if (jlen == 8) return QSP_OEF(8, true);
+      if (jlen == 4) return QSP_OEF(4, true);
+    }
     if (np == 1) {
       if (jlen <= 2) return QSP_OE(2, 1, true);
       if (jlen <= 4) return QSP_OE(4, 1, true);
@@ -437,6 +450,7 @@ __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, 
     if (jlen <= 8) return QSP_OE(8, 2, false);
     return false;  // unreachable: geometry limits np = 2 to 8 columns per lane
 #undef QSP_OE
+#undef QSP_OEF
   }
   int cap_rows = cap_elems / ldw;
   if (cap_rows < 2) cap_rows = 2;

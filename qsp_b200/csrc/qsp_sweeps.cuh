@@ -298,6 +298,7 @@ struct RCompressArgs {
   int32_t* status;          // [B]
   cplx* work;               // per-CTA scratch, rcompress_work_elems() each
   long work_stride;         // elements per CTA
+  int* queue;               // instance queue head (zeroed before the launch): CTAs pull instances dynamically
   int cap_rows_elems;       // shared elements available for Jacobi rows
   int tpp;                  // lanes per Jacobi pair
   int max_sweeps;
@@ -348,7 +349,14 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
 #define QSP_TICK() (tck = qsp_clock())
 #define QSP_TOCK(slot) (pc[slot] += qsp_clock() - tck, tck = qsp_clock())
 
-  for (int inst = blockIdx.x; inst < P.B; inst += gridDim.x) {
+  // dynamic instance queue: Jacobi sweep counts differ per instance, so CTAs pull work instead of striding
+  int* s_inst = (int*)(red + 56);
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) *s_inst = atomicAdd(P.queue, 1);
+    __syncthreads();
+    const int inst = *s_inst;
+    if (inst >= P.B) break;
     const cplx* A = P.in + (long)inst * L * sin;
     const int32_t* bi = P.bonds_in + (long)inst * (L + 1);
     cplx* O = P.out + (long)inst * L * sout;

@@ -152,6 +152,11 @@ inline int __shfl_xor_sync(unsigned m, int v, int mask, int width = 32) {
   return (int)__shfl_xor_sync(m, (double)v, mask, width);
 }
 inline void __threadfence_block() {}
+inline int atomicAdd(int* p, int v) {
+  int o = *p;
+  *p = o + v;
+  return o;
+}
 inline void emu_named_barrier(int id, int count) { emu::group_sync(emu::g_blk->named[id & 15], (unsigned)count); }
 inline void emu_spin_yield() { emu::yield(); }
 inline char* emu_dynamic_smem() {
