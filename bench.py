@@ -414,19 +414,24 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     peak = fp64_peak(torch, lib, dev, sms)
     achieved = alg / (dur_ms * 1e-3) / 1e12
-    traffic, traffic_src = None, None
+    traffic, traffic_src, ncu_fp64 = None, None, None
     try:  # dram__bytes_read+write of this kernel from the committed ncu capture, scaled to this launch's batch
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("config") == f"L{L} chi{chi} layers4" or tj.get("config") == f"L{L} chi{chi} layers{a.layers}":
             traffic = tj["dram_bytes_per_instance"] * B
             traffic_src = f"ncu dram__bytes_read.sum+dram__bytes_write.sum at batch {tj['batch']} ({tj['source']}), scaled to batch {B}"
+            ncu_fp64 = tj.get("fp64_pipe_busy_pct_ncu")
     except Exception:  # noqa: BLE001
         pass
     layer_ms = sum(v for k, v in times.items())
     return {"bound": "fp64", "kernel": "k_right_compress(2chi->chi)", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+            "note": "achieved counts the REFERENCE's flops this launch replaces (S2+S3+S4 of SURVEY 8d: inverse layer with "
+                    "SVD splits, two 2chi QR sweeps, two SVD sweeps); the device reaches the same state with one Jacobi sweep "
+                    "(DESIGN.md I1-I3), so frac is an algorithmic speed figure, not pipe utilisation",
+            "fp64_pipe_busy_pct_ncu": ncu_fp64,
             "algorithmic_flops_per_launch": alg, "kernel_ms": dur_ms,
             "layer_kernel_ms": {k: round(v, 3) for k, v in times.items()},
             "kernel_share_of_layer": dur_ms / layer_ms if layer_ms else None,
