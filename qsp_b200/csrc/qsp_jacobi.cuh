@@ -433,12 +433,17 @@ __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, 
     const int s_off = (int)((char*)Wsm - QSP_SMEM_BASE()), r_off = (int)((char*)red - QSP_SMEM_BASE());
 #define QSP_OE(C, N, H) \
   jacobi_rows_oe<C, N, H>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
-#define QSP_OEF(C, H) \
-  jacobi_rows_oe<C, 1, H, 8, true>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
-    if (np == 1 && tpp == 8 && jdot == jlen) {  // square power-of-two problems of the layer loop
-      if (jlen == 16) return QSP_OEF(16, false);
-      if (jlen == 8) return QSP_OEF(8, true);
-      if (jlen == 4) return QSP_OEF(4, true);
+#define QSP_OEF(C, H, T) \
+  jacobi_rows_oe<C, 1, H, T, true>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
+    if (np == 1 && jdot == jlen) {  // power-of-two problems of the layer loop and of the input pipeline
+      if (tpp == 8) {
+        if (jlen == 16) return QSP_OEF(16, false, 8);  // 128 x 128 (chi = 64 bulk)
+        if (jlen == 8) return QSP_OEF(8, true, 8);     // 64 x 64 (chi = 32)
+        if (jlen == 4) return QSP_OEF(4, true, 8);     // 32 x 32 (chi = 16)
+      } else if (tpp == 16) {
+        if (jlen == 8) return QSP_OEF(8, true, 16);    // 64 x 128 (prepare_target / second pass at chi = 64)
+        if (jlen == 4) return QSP_OEF(4, true, 16);    // 32 x 64
+      }
     }
     if (np == 1) {
       if (jlen <= 2) return QSP_OE(2, 1, true);
