@@ -21,15 +21,18 @@ __host__ __device__ inline size_t qsp_gemm_smem_bytes(int nt) {
 }
 
 // Must be called by all threads of the block (contains __syncthreads).
-__device__ inline void cta_zgemm(int m, int n, int kdim, const cplx* __restrict__ A, long sAr, long sAk, bool conjA,
-                                 const cplx* __restrict__ B, long sBk, long sBc, bool conjB, cplx* __restrict__ C,
-                                 long sCr, long sCc, bool accumulate, cplx* tiles) {
-  const int nt = blockDim.x, tid = threadIdx.x;
-  const int TM = 4 * (nt / 16), TN = QSP_GEMM_TN, TK = QSP_GEMM_TK;
-  const int ldA = TM + 1, ldB = TN + 1;
+// NT = blockDim.x at compile time (tile geometry and shared strides become immediates).
+template <int NT>
+__device__ __forceinline__ void cta_zgemm_t(int m, int n, int kdim, const cplx* __restrict__ A, long sAr, long sAk,
+                                            bool conjA, const cplx* __restrict__ B, long sBk, long sBc, bool conjB,
+                                            cplx* __restrict__ C, long sCr, long sCc, bool accumulate, cplx* tiles) {
+  constexpr int TM = 4 * (NT / 16), TN = QSP_GEMM_TN, TK = QSP_GEMM_TK;
+  constexpr int ldA = TM + 1, ldB = TN + 1;
+  const int tid = threadIdx.x;
   cplx* As = tiles;             // [TK][ldA]
   cplx* Bs = tiles + TK * ldA;  // [TK][ldB]
   const int tx = tid & 15, ty = tid >> 4;
+  const bool unitA = (sAk == 1), unitB = (sBk == 1);
 
   for (int i0 = 0; i0 < m; i0 += TM) {
     for (int j0 = 0; j0 < n; j0 += TN) {
@@ -38,12 +41,14 @@ __device__ inline void cta_zgemm(int m, int n, int kdim, const cplx* __restrict_
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = cmake(0.0, 0.0);
+      const bool active = (i0 + ty * 4 < m) && (j0 + tx * 4 < n);
 
       for (int k0 = 0; k0 < kdim; k0 += TK) {
         __syncthreads();
-        for (int idx = tid; idx < TM * TK; idx += nt) {
+#pragma unroll
+        for (int idx = tid; idx < TM * TK; idx += NT) {
           int r, kk;
-          if (sAk == 1) {
+          if (unitA) {
             kk = idx % TK;
             r = idx / TK;
           } else {
@@ -57,9 +62,10 @@ __device__ inline void cta_zgemm(int m, int n, int kdim, const cplx* __restrict_
           }
           As[kk * ldA + r] = v;
         }
-        for (int idx = tid; idx < TN * TK; idx += nt) {
+#pragma unroll
+        for (int idx = tid; idx < TN * TK; idx += NT) {
           int c, kk;
-          if (sBk == 1) {
+          if (unitB) {
             kk = idx % TK;
             c = idx / TK;
           } else {
@@ -74,7 +80,7 @@ __device__ inline void cta_zgemm(int m, int n, int kdim, const cplx* __restrict_
           Bs[kk * ldB + c] = v;
         }
         __syncthreads();
-        if (i0 + ty * 4 < m && j0 + tx * 4 < n) {
+        if (active) {
 #pragma unroll
           for (int kk = 0; kk < TK; ++kk) {
             cplx a[4], b[4];
@@ -109,4 +115,15 @@ __device__ inline void cta_zgemm(int m, int n, int kdim, const cplx* __restrict_
     }
   }
   __syncthreads();
+}
+
+__device__ inline void cta_zgemm(int m, int n, int kdim, const cplx* __restrict__ A, long sAr, long sAk, bool conjA,
+                                 const cplx* __restrict__ B, long sBk, long sBc, bool conjB, cplx* __restrict__ C,
+                                 long sCr, long sCc, bool accumulate, cplx* tiles) {
+  switch (blockDim.x) {
+    case 512: cta_zgemm_t<512>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
+    case 256: cta_zgemm_t<256>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
+    case 128: cta_zgemm_t<128>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
+    default: cta_zgemm_t<64>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
+  }
 }
