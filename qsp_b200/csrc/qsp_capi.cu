@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(NTMAX) k_jacobi_bench(cplx* W, int nrows, int 
 // in 128 registers), so that latency is hidden by instruction-level parallelism instead of warps.
 __global__ void __launch_bounds__(256) k_jacobi_bench_fat(cplx* W, int nrows, int ldw, int B, int* sweeps, int* ok) {
   char* sm = QSP_SMEM_BASE();
-  const int cap_elems = ((nrows + 1) / 2) * ldw;
+  const int ne_ = (nrows + 1) / 2;
+  const int cap_elems = ne_ * ldw + (ne_ + 1) / 2 + 1;
   double* red = (double*)(sm + (size_t)cap_elems * sizeof(cplx));
   const int tpp = 4;
   for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(256) k_jacobi_bench_fat(cplx* W, int nrows, in
 extern "C" int qsp_jacobi_bench_fat(qsp_c128* W, int nrows, int ldw, int B, int* sweeps, int* ok, void* stream) {
   DevInfo d = dev_info();
   if (nrows / 2 > 64 || ldw != 128) return QSP_ERR_ARG;
-  size_t smem = (size_t)((nrows + 1) / 2) * ldw * sizeof(cplx) + 64 * sizeof(double) + 64;
+  size_t smem = ((size_t)((nrows + 1) / 2) * ldw + (nrows + 3) / 4 + 1) * sizeof(cplx) + 64 * sizeof(double) + 64;
   int grid = B < d.sms ? B : d.sms;
   QSP_PREP_KERNEL(k_jacobi_bench_fat, smem);
   QSP_LAUNCH(k_jacobi_bench_fat, grid, 256, smem, (qsp_stream_t)stream, (cplx*)W, nrows, ldw, B, sweeps, ok);

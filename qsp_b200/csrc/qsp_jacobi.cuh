@@ -225,9 +225,20 @@ __device__ __forceinline__ void jacobi_rotation(double al, double be, double gx,
 // TPPC > 0 fixes the team width at compile time and FULL asserts jdot == jlen == CPL (no column
 // predicates): the square power-of-two cases of the layer loop get immediate shared-memory offsets
 // and noticeably lower register pressure.
+//
+// Scaled ("fast") rotations: every row is stored as d * x~ with a real scale d kept beside it
+// (register rows: dr[], shared rows: dS[slot]).  With t e^{i phi} = w g the rotation
+//     x' = c (x - w g y),  y' = c (y + w conj(g) x)
+// becomes  x~' = x~ - (w dr^2 g~) y~,  d_x' = c ds ;   y~' = y~ + (w ds^2 conj(g~)) x~,  d_y' = c dr,
+// i.e. two complex multiply-adds per column (8 DFMA) instead of 12 flops-heavy instructions.  The
+// convergence test |g|^2 <= tol^2 alpha beta is scale free.  Scales are folded back into the data at
+// the end of every sweep (they only shrink, by c >= 1/sqrt 2 per rotation).
+// They are used where both rows of a visit are register resident (HOLD); the 16-columns-per-lane
+// variant sits at the 128-register limit and keeps plain rotations (the extra scalars spill).
 template <int CPL, int NP, bool HOLD, int TPPC = 0, bool FULL = false>
 __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int jlen_, int s_off, int tpp_, double tol2,
                                             int max_sweeps, int red_off, int* sweeps_out) {
+  constexpr bool FAST = HOLD;
   const int tpp = TPPC > 0 ? TPPC : tpp_;
   const int jlen = FULL ? CPL : jlen_;
   const int jdot = FULL ? CPL : jdot_;
@@ -237,10 +248,13 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
   const int team = tid / tpp, tl = tid % tpp;
   const int ldw = jlen * tpp;
   const int ne = (nrows + 1) >> 1, no = nrows >> 1;
+  double* dS = (double*)(S + (long)ne * ldw);  // scales of the shared (even-position) rows
   cplx R[NP][CPL];
+  double dr[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) {
     const int p = team * NP + q;
+    dr[q] = 1.0;
 #pragma unroll
     for (int j = 0; j < CPL; ++j)
       R[q][j] = (p < no && j < jlen) ? Wg[(long)(2 * p + 1) * ldw + tl + j * tpp] : cmake(0.0, 0.0);
@@ -249,6 +263,7 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
     const int r = idx / ldw, c = idx - r * ldw;
     S[idx] = Wg[(long)(2 * r) * ldw + c];
   }
+  for (int idx = tid; idx < ne; idx += nt) dS[idx] = 1.0;
   __syncthreads();
   bool conv = false;
   int sweeps = 0;
@@ -264,13 +279,14 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
         const int slot = p + (r & 1);
         const bool valid = (p < no) && (slot < ne);
         cplx* xs = S + (long)(valid ? slot : 0) * ldw + tl;
+        const double ds = FAST ? dS[valid ? slot : 0] : 1.0;
         cplx x[HOLD ? CPL : 1];
         if (HOLD) {
 #pragma unroll
           for (int j = 0; j < CPL; ++j)
             if (j < jlen) x[HOLD ? j : 0] = xs[j * tpp];
         }
-        double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
+        double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;  // Gram entries of the scaled rows
         if (HOLD) {
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
@@ -320,16 +336,24 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
             gx += shfl_xor_d(gx, o);
             gy += shfl_xor_d(gy, o);
           }
+        if (FAST) __syncwarp();  // every lane of the team has read dS[slot] before it is rewritten below
         if (valid) {
-          const double g2 = gx * gx + gy * gy;
-          const double ab = al * be;
-          if ((jv & 8) ? false : ((jv & 4) ? true : (ab > 1e-280 && g2 > tol2 * ab))) {
-            double cs, sx, sy;
-            if (jv & 4) {
-              cs = 0.8, sx = 0.6, sy = 0.0;
-            } else
-              jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
-            if (tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) *flag = 1;
+          const double g2t = gx * gx + gy * gy;
+          const double abt = al * be;
+          if ((jv & 8) ? false : ((jv & 4) ? true : (abt > 1e-280 && g2t > tol2 * abt))) {
+            // true Gram entries: alpha = ds^2 al, beta = dr^2 be, |g|^2 = ds^2 dr^2 |g~|^2
+            const double ds2 = FAST ? ds * ds : 1.0, dr2 = FAST ? dr[q] * dr[q] : 1.0;
+            const double A = ds2 * al, Bq = dr2 * be, g2 = ds2 * dr2 * g2t;
+            const double d = Bq - A;
+            const double h = sqrt(fma(d, d, 4.0 * g2));
+            const double w = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);  // t e^{i phi} = w g
+            const double cs = qsp_rsqrt(fma(w * w, g2, 1.0));
+            // FAST: tau1 = w dr^2 g~, tau2 = w ds^2 conj(g~) = (t2x, -t2y);  plain: s e^{i phi} = c w g
+            const double w1 = FAST ? w * dr2 : cs * w, w2 = FAST ? w * ds2 : cs * w;
+            const double t1x = w1 * gx, t1y = w1 * gy;
+            const double t2x = w2 * gx, t2y = w2 * gy;
+            const double c0 = FAST ? 1.0 : cs;  // plain rotations scale the kept term by c
+            if (tl == 0 && g2t > (QSP_JAC_QUAD * QSP_JAC_QUAD) * abt) *flag = 1;
             if (HOLD) {
 #pragma unroll
               for (int j = 0; j < CPL; ++j) {
@@ -337,10 +361,10 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
                   const cplx y = R[q][j];
                   const cplx xv = x[HOLD ? j : 0];
                   cplx xn, yn;
-                  xn.x = fma(cs, xv.x, fma(sy, y.y, -sx * y.x));
-                  xn.y = fma(cs, xv.y, -fma(sx, y.y, sy * y.x));
-                  yn.x = fma(cs, y.x, fma(sx, xv.x, sy * xv.y));
-                  yn.y = fma(cs, y.y, fma(sx, xv.y, -sy * xv.x));
+                  xn.x = fma(-t1x, y.x, fma(t1y, y.y, FAST ? xv.x : c0 * xv.x));
+                  xn.y = fma(-t1x, y.y, fma(-t1y, y.x, FAST ? xv.y : c0 * xv.y));
+                  yn.x = fma(t2x, xv.x, fma(t2y, xv.y, FAST ? y.x : c0 * y.x));
+                  yn.y = fma(t2x, xv.y, fma(-t2y, xv.x, FAST ? y.y : c0 * y.y));
                   xs[j * tpp] = yn;  // the rows trade places
                   R[q][j] = xn;
                 }
@@ -358,15 +382,19 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
                     const cplx y = R[q][j0 + u];
                     const cplx xv = xt[u];
                     cplx xn, yn;
-                    xn.x = fma(cs, xv.x, fma(sy, y.y, -sx * y.x));
-                    xn.y = fma(cs, xv.y, -fma(sx, y.y, sy * y.x));
-                    yn.x = fma(cs, y.x, fma(sx, xv.x, sy * xv.y));
-                    yn.y = fma(cs, y.y, fma(sx, xv.y, -sy * xv.x));
+                    xn.x = fma(-t1x, y.x, fma(t1y, y.y, FAST ? xv.x : c0 * xv.x));
+                    xn.y = fma(-t1x, y.y, fma(-t1y, y.x, FAST ? xv.y : c0 * xv.y));
+                    yn.x = fma(t2x, xv.x, fma(t2y, xv.y, FAST ? y.x : c0 * y.x));
+                    yn.y = fma(t2x, xv.y, fma(-t2y, xv.x, FAST ? y.y : c0 * y.y));
                     xs[(j0 + u) * tpp] = yn;  // the rows trade places
                     R[q][j0 + u] = xn;
                   }
                 }
               }
+            }
+            if (FAST) {
+              if (tl == 0) dS[slot] = cs * dr[q];  // scale of the row that moved to shared memory (y')
+              dr[q] = cs * ds;                     // scale of the row that moved to registers (x')
             }
           } else {
 #pragma unroll
@@ -377,10 +405,25 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
                 R[q][j] = xv;
               }
             }
+            if (FAST) {
+              if (tl == 0) dS[slot] = dr[q];
+              dr[q] = ds;
+            }
           }
         }
       }
       if (!(jv & 16)) __syncthreads();
+    }
+    if (FAST) {  // fold the scales back into the data (keeps them away from underflow)
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) R[q][j] = cscale(R[q][j], dr[q]);
+        dr[q] = 1.0;
+      }
+      for (int idx = tid; idx < ne * ldw; idx += nt) S[idx] = cscale(S[idx], dS[idx / ldw]);
+      __syncthreads();
+      for (int idx = tid; idx < ne; idx += nt) dS[idx] = 1.0;
     }
     ++sweeps;
     if (jv) {
@@ -388,7 +431,7 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
       if (sweeps >= 8) break;
       continue;
     }
-    if (*flag == 0) {  // (the round loop ended with a barrier)
+    if (*flag == 0) {  // (ordered by the barrier above)
       conv = true;
       break;
     }
@@ -415,7 +458,8 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
 __host__ __device__ inline bool jacobi_oe_fits(int nt, int nrows, int ldw, int cap_elems) {
   int tpp, np;
   if (!jacobi_oe_geometry(nt, nrows, ldw, &tpp, &np)) return false;
-  return (long)((nrows + 1) >> 1) * ldw <= cap_elems;
+  const long ne = (nrows + 1) >> 1;
+  return ne * ldw + (ne + 1) / 2 <= cap_elems;  // even rows + their scales
 }
 
 // Dispatcher.  Wg: nrows x ldw (row stride ldw), first ndotp columns enter the Gram entries;
@@ -428,7 +472,7 @@ __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, 
   }
   const int nt = blockDim.x;
   int tpp, np;
-  if (jacobi_oe_geometry(nt, nrows, ldw, &tpp, &np) && (long)((nrows + 1) >> 1) * ldw <= cap_elems) {
+  if (jacobi_oe_geometry(nt, nrows, ldw, &tpp, &np) && jacobi_oe_fits(nt, nrows, ldw, cap_elems)) {
     const int jlen = ldw / tpp, jdot = (ndotp + tpp - 1) / tpp;
     const int s_off = (int)((char*)Wsm - QSP_SMEM_BASE()), r_off = (int)((char*)red - QSP_SMEM_BASE());
 #define QSP_OE(C, N, H) \
