@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) k_jacobi_bench_fat(cplx* W, int nrows, in
   for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
     int ns = 0;
     const double tol = 4e-16 * sqrt((double)ldw);
-    bool c = jacobi_rows_oe<32, 1, false>(W + (long)inst * nrows * ldw, nrows, ldw / tpp, ldw / tpp, 0, tpp, tol * tol, 60,
+    bool c = jacobi_rows_oe<32, 1, false, 4, true, 1>(W + (long)inst * nrows * ldw, nrows, ldw / tpp, ldw / tpp, 0, tpp, tol * tol, 60,
                                           (int)((char*)red - sm), &ns);
     if (threadIdx.x == 0) {
       sweeps[inst] = ns;

@@ -181,7 +181,10 @@ __device__ int g_jvar = 0;
 #else
 #define QSP_JV() (0)
 #endif
-#define QSP_JCH 2    // columns of the shared row fetched per batch in the streaming (non-HOLD) path
+#ifndef QSP_JCH
+#define QSP_JCH 2
+#endif
+//   // columns of the shared row fetched per batch in the streaming (non-HOLD) path
 #define QSP_JPAD 32
 // A sweep whose largest rotated |g|/sqrt(alpha beta) is <= QSP_JAC_QUAD leaves off-diagonals of
 // order n * QSP_JAC_QUAD^2 ~ 1e-16 (quadratic convergence): no verification sweep is needed.
@@ -235,10 +238,10 @@ __device__ __forceinline__ void jacobi_rotation(double al, double be, double gx,
 // the end of every sweep (they only shrink, by c >= 1/sqrt 2 per rotation).
 // They are used where both rows of a visit are register resident (HOLD); the 16-columns-per-lane
 // variant sits at the 128-register limit and keeps plain rotations (the extra scalars spill).
-template <int CPL, int NP, bool HOLD, int TPPC = 0, bool FULL = false>
+template <int CPL, int NP, bool HOLD, int TPPC = 0, bool FULL = false, int FASTSEL = -1>
 __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int jlen_, int s_off, int tpp_, double tol2,
                                             int max_sweeps, int red_off, int* sweeps_out) {
-  constexpr bool FAST = HOLD;
+  constexpr bool FAST = FASTSEL < 0 ? HOLD : (FASTSEL != 0);
   const int tpp = TPPC > 0 ? TPPC : tpp_;
   const int jlen = FULL ? CPL : jlen_;
   const int jdot = FULL ? CPL : jdot_;
@@ -477,8 +480,12 @@ __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, 
     const int s_off = (int)((char*)Wsm - QSP_SMEM_BASE()), r_off = (int)((char*)red - QSP_SMEM_BASE());
 #define QSP_OE(C, N, H) \
   jacobi_rows_oe<C, N, H>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
+#ifndef QSP_MAIN_FAST
+#define QSP_MAIN_FAST 0  // scaled rotations in the 16-columns-per-lane variant (register limited: off)
+#endif
 #define QSP_OEF(C, H, T) \
-  jacobi_rows_oe<C, 1, H, T, true>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
+  jacobi_rows_oe<C, 1, H, T, true, ((C) == 16 ? QSP_MAIN_FAST : -1)>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, \
+                                                                       r_off, sweeps_out)
     if (np == 1 && jdot == jlen) {  // power-of-two problems of the layer loop and of the input pipeline
       if (tpp == 8) {
         if (jlen == 16) return QSP_OEF(16, false, 8);  // 128 x 128 (chi = 64 bulk)
