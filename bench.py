@@ -49,15 +49,18 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--second-pass", action="store_true")
-    ap.add_argument("--workload", default="random", choices=["random", "heisenberg"],
+    ap.add_argument("--workload", default="random", choices=["random", "heisenberg", "aklt"],
                     help="random: SURVEY 8d synthetic MPS; heisenberg: the reference's L=32 ground state "
-                         "(tests/golden/heisenberg_L32.npz) replicated over the batch (cfg 3a: --layers 6 --chi 32)")
+                         "(tests/golden/heisenberg_L32.npz) replicated over the batch (cfg 3a: --layers 6 --chi 32); "
+                         "aklt: make_aklt_mps(L/2) + make_splitted_mps replicated (cfg 3b: --L 100 --layers 6 --chi 32)")
     return ap.parse_args()
 
 
 def workload_name(a):
     if a.workload == "heisenberg":
         return f"heisenberg_L32_pickle_replicated_layers{a.layers}_compress_maxbond{a.chi}"
+    if a.workload == "aklt":
+        return f"aklt_L{a.L}_qubits_replicated_layers{a.layers}_compress_maxbond{a.chi}"
     return f"random_mps_L{a.L}_chi{a.chi}_d2_layers{a.layers}_compress_maxbond{a.chi}"
 
 
@@ -189,6 +192,19 @@ class ClockSampler:
         return out
 
 
+def aklt_batch(torch, B, L, chi, dev):
+    """cfg 3b: AKLT chain of L/2 spin-1 sites split into L qubits (qsp_b200.misc_states), replicated."""
+    from qsp_b200.engine import pack_mps_list
+    from qsp_b200.misc_states import make_aklt_mps, make_splitted_mps
+    from qsp_b200.mps import to_lpr
+
+    tens, _ = make_aklt_mps(L // 2)
+    arr, b = pack_mps_list([to_lpr(make_splitted_mps(tens), "lrp")], chi)
+    x = torch.from_numpy(arr).to(dev).repeat(B, 1, 1, 1, 1).contiguous()
+    bonds = torch.from_numpy(b).to(dev).repeat(B, 1).contiguous()
+    return x, bonds
+
+
 def synth_batch(torch, B, L, chi, dev, seed):
     """Random complex MPS with bond profile min(chi, 2^i, 2^(L-i)), entries N(0,1)+iN(0,1)
     (SURVEY.md section 8d), generated on the device; padding zero."""
@@ -231,6 +247,8 @@ def main():
     if a.workload == "heisenberg":
         raw, bonds0 = heisenberg_batch(torch, B, chi, dev)
         L = a.L = raw.shape[1]
+    elif a.workload == "aklt":
+        raw, bonds0 = aklt_batch(torch, B, L, chi, dev)
     else:
         raw, bonds0 = synth_batch(torch, B, L, chi, dev, 1234 + rank)
     tgt, tb = raw.clone(), bonds0.clone()

@@ -25,6 +25,10 @@ def one(args):
                                  "heisenberg_L32.npz"))
         b, m = z["bonds"], z["mps"]
         raw = [m[i, : b[i], :, : b[i + 1]].copy() for i in range(len(b) - 1)]
+    elif WORKLOAD == "aklt":
+        from qsp_b200.misc_states import make_aklt_mps, make_splitted_mps
+
+        raw = O.to_lpr(make_splitted_mps(make_aklt_mps(L // 2)[0]), "lrp")
     else:
         raw = O.random_mps(L, chi, seed)
     t = O.prepare_target(raw, "lpr")
