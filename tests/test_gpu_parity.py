@@ -223,6 +223,16 @@ def test_pipeline_six_layers_heisenberg(drv):
     _check_pipeline(drv, [_prepared(mps)], 6, 32, 32, same_convention=False)
 
 
+def test_pipeline_aklt(drv):
+    """AKLT chain (examples/state_prep_examples.py:14-17): 6 spin-1 sites split into 12 qubits, 3 layers,
+    no compression.  Teacher-forced only: the near-degenerate triplet at the D=2 cut makes the D=2 state
+    itself ill-conditioned, so LAPACK and Jacobi may keep different vectors."""
+    from qsp_b200.misc_states import make_aklt_mps, make_splitted_mps
+
+    raw = O.to_lpr(make_splitted_mps(make_aklt_mps(6)[0]), "lrp")
+    _check_pipeline(drv, [_prepared(raw)], 3, 0, 32, same_convention=False, check_svals=False)
+
+
 def test_golden_heisenberg_layer1(drv):
     """reference pickle examples/data/heisenberg_L32_dist0.8000.pkl: layer-1 overlap
     0.5704604532578025 (gauge invariant), depths/gate_counts [32, ...]."""
