@@ -127,9 +127,9 @@ static bool plan_rcompress(int Din, int Dout, const DevInfo& d, RCompressPlan* p
   long cmax = imin(2 * Dout, Din - 1);
   long needC = cmax > 0 ? cmax * (r32(Din) + r32(cmax)) : 0;
   long need = needR > needC ? needR : needC;
-  size_t fixed = rcompress_smem_bytes(0, Dout, p->nt) - qsp_gemm_smem_bytes(p->nt);
+  size_t fixed = rcompress_smem_bytes(0, Dout, p->nt) - qsp_gemm_smem_bytes(p->nt, QSP_GEMM_TK_DEEP);
   long budget = ((long)d.max_smem - (long)fixed) / (long)sizeof(cplx);
-  long gem = (long)(qsp_gemm_smem_bytes(p->nt) / sizeof(cplx));
+  long gem = (long)(qsp_gemm_smem_bytes(p->nt, QSP_GEMM_TK_DEEP) / sizeof(cplx));
   if (budget < gem) return false;
   // at least two rows of the longest possible row must fit
   long maxlen = imax((int)r32(2 * Dout), (int)(r32(Din) + r32(cmax)));

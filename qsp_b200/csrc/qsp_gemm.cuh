@@ -15,18 +15,18 @@
 #define QSP_GEMM_TN 64
 
 // bytes of shared memory cta_zgemm needs for a block of nt threads
-__host__ __device__ inline size_t qsp_gemm_smem_bytes(int nt) {
+__host__ __device__ inline size_t qsp_gemm_smem_bytes(int nt, int tk = QSP_GEMM_TK) {
   int tm = 4 * (nt / 16);
-  return (size_t)QSP_GEMM_TK * ((tm + 1) + (QSP_GEMM_TN + 1)) * sizeof(cplx);
+  return (size_t)tk * ((tm + 1) + (QSP_GEMM_TN + 1)) * sizeof(cplx);
 }
 
 // Must be called by all threads of the block (contains __syncthreads).
 // NT = blockDim.x at compile time (tile geometry and shared strides become immediates).
-template <int NT>
+template <int NT, int TK = QSP_GEMM_TK>
 __device__ __forceinline__ void cta_zgemm_t(int m, int n, int kdim, const cplx* __restrict__ A, long sAr, long sAk,
                                             bool conjA, const cplx* __restrict__ B, long sBk, long sBc, bool conjB,
                                             cplx* __restrict__ C, long sCr, long sCc, bool accumulate, cplx* tiles) {
-  constexpr int TM = 4 * (NT / 16), TN = QSP_GEMM_TN, TK = QSP_GEMM_TK;
+  constexpr int TM = 4 * (NT / 16), TN = QSP_GEMM_TN;
   constexpr int ldA = TM + 1, ldB = TN + 1;
   const int tid = threadIdx.x;
   cplx* As = tiles;             // [TK][ldA]
@@ -125,5 +125,19 @@ __device__ inline void cta_zgemm(int m, int n, int kdim, const cplx* __restrict_
     case 256: cta_zgemm_t<256>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
     case 128: cta_zgemm_t<128>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
     default: cta_zgemm_t<64>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
+  }
+}
+
+// Deeper k-tiles (half the barriers and exposed load latencies per flop) for kernels that can
+// spare the shared memory: qsp_gemm_smem_bytes(nt, QSP_GEMM_TK_DEEP).
+#define QSP_GEMM_TK_DEEP 16
+__device__ inline void cta_zgemm_deep(int m, int n, int kdim, const cplx* __restrict__ A, long sAr, long sAk, bool conjA,
+                                      const cplx* __restrict__ B, long sBk, long sBc, bool conjB, cplx* __restrict__ C,
+                                      long sCr, long sCc, bool accumulate, cplx* tiles) {
+  switch (blockDim.x) {
+    case 512: cta_zgemm_t<512, QSP_GEMM_TK_DEEP>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
+    case 256: cta_zgemm_t<256, QSP_GEMM_TK_DEEP>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
+    case 128: cta_zgemm_t<128, QSP_GEMM_TK_DEEP>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
+    default: cta_zgemm_t<64, QSP_GEMM_TK_DEEP>(m, n, kdim, A, sAr, sAk, conjA, B, sBk, sBc, conjB, C, sCr, sCc, accumulate, tiles); return;
   }
 }

@@ -314,7 +314,7 @@ __host__ __device__ inline long rcompress_work_elems(int Din, int Dout) {
 // shared: Jacobi rows | gemm tiles (aliased onto the same area) + norms/perm + red
 __host__ __device__ inline size_t rcompress_smem_bytes(int jac_elems, int Dout, int nt) {
   size_t a = (size_t)jac_elems * sizeof(cplx);
-  size_t g = qsp_gemm_smem_bytes(nt);
+  size_t g = qsp_gemm_smem_bytes(nt, QSP_GEMM_TK_DEEP);
   size_t s = a > g ? a : g;
   s += (size_t)(2 * Dout) * (sizeof(double) + sizeof(int));  // norms + perm
   s += 64 * sizeof(double);
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
   const int Din = P.Din, Dout = P.Dout, L = P.L;  // padded strides of the in / out buffers
   const int DinL = P.DinL, DoutL = P.DoutL;       // live bounds: scratch and shared-memory sizing
   size_t jac_bytes = (size_t)P.cap_rows_elems * sizeof(cplx);
-  size_t gem_bytes = qsp_gemm_smem_bytes(nt);
+  size_t gem_bytes = qsp_gemm_smem_bytes(nt, QSP_GEMM_TK_DEEP);
   size_t big = jac_bytes > gem_bytes ? jac_bytes : gem_bytes;
   cplx* Wsm = (cplx*)sm;
   cplx* tiles = (cplx*)sm;  // aliased: GEMMs and Jacobi never overlap in time
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         }
         __syncthreads();
       } else {
-        cta_zgemm(2 * b, rp, ro, Ai, Din, 1, false, Cg, DoutL, 1, false, Mg, rp, 1, false, tiles);
+        cta_zgemm_deep(2 * b, rp, ro, Ai, Din, 1, false, Cg, DoutL, 1, false, Mg, rp, 1, false, tiles);
       }
       if (i == 0) {
         // orthogonality centre: site 0 <- M (b x 2 x rp), optional normalisation
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         }
         __syncthreads();
         // U s = M Vh^H
-        cta_zgemm(b, k, c, Mg, c, 1, false, Vg, 1, c, true, Cg, DoutL, 1, false, tiles);
+        cta_zgemm_deep(b, k, c, Mg, c, 1, false, Vg, 1, c, true, Cg, DoutL, 1, false, tiles);
       }
       QSP_TOCK(4);
       // ---- <0...0| amplitude: f_new[q] = sum_kk Vh[q,(0,kk)] f[kk] ---------------------------
