@@ -85,6 +85,17 @@ int qsp_generate_unitaries(qsp_c128* d2, const int32_t* d2_bonds, int B, int L, 
 int qsp_apply_inverse_layer(const qsp_c128* in, const int32_t* bonds_in, int D_in, const qsp_c128* G,
                             const int32_t* kind, qsp_c128* out, int32_t* bonds_out, int D_out, int B, int L,
                             int32_t* status, void* stream);
+/* Fused gate-apply-and-split: apply_inverse_unitary_layer_on_wfn (core.py:224-240) followed by
+ * [right_canonize; compress('right', max_bond)] (sequential.py:52-54) in one right-to-left sweep over
+ * a LEFT-canonical psi (D-padded in and out, out != in).  The doubled tensors of U^dagger psi are never
+ * stored: site t of U^dagger psi is G_{t-1}^dagger o A_{t-1}, so the sweep forms M = A_{t-1} C, mixes it
+ * with the 4x4 gate and splits it with the Jacobi SVD.  amp0 as in qsp_right_compress. */
+size_t qsp_apply_inverse_and_compress_workspace_bytes(int B, int L, int D);
+int qsp_apply_inverse_and_compress(const qsp_c128* in, const int32_t* bonds_in, const qsp_c128* G, const int32_t* kind,
+                                   qsp_c128* out, int32_t* bonds_out, int D, int B, int L, int max_bond, double cutoff,
+                                   int normalize, qsp_c128* amp0, int32_t* status, void* work, size_t work_bytes,
+                                   void* stream);
+
 /* the gate application of apply_unitary_layer_on_wfn (core.py:126-138) on a
  * RIGHT-canonical MPS, exact; the `compress('right')` of core.py:140 is
  * qsp_left_canonize + qsp_right_compress on the result. */

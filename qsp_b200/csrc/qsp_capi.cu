@@ -194,10 +194,17 @@ extern "C" size_t qsp_right_compress_workspace_bytes(int B, int L, int D_in, int
 static int right_compress_live(const qsp_c128* in, const int32_t* bonds_in, int D_in, qsp_c128* out,
                                int32_t* bonds_out, int D_out, int DinL, int DoutL, int B, int L, int max_bond,
                                double cutoff, int normalize, double* svals, int nsv, qsp_c128* amp0, int32_t* status,
-                               void* work, size_t work_bytes, void* stream) {
+                               void* work, size_t work_bytes, void* stream, const qsp_c128* G = nullptr,
+                               const int32_t* kind = nullptr) {
   if (!in || !bonds_in || !out || !bonds_out || !work || B <= 0 || L <= 0 || D_in <= 0 || D_out <= 0)
     return QSP_ERR_ARG;
-  if (DinL <= 0 || DinL > D_in) DinL = D_in;
+  const bool fused = G != nullptr;
+  if (fused && (!kind || D_in > D_out || in == out || bonds_in == bonds_out)) return QSP_ERR_ARG;
+  if (fused) {
+    if (DinL <= 0) DinL = 2 * D_in;  // live bonds of U^dagger psi
+  } else if (DinL <= 0 || DinL > D_in) {
+    DinL = D_in;
+  }
   if (DoutL <= 0 || DoutL > D_out) DoutL = D_out;
   DevInfo d = dev_info();
   RCompressPlan p;
@@ -228,6 +235,8 @@ static int right_compress_live(const qsp_c128* in, const int32_t* bonds_in, int 
   a.work = (cplx*)((char*)work + 256);
   a.work_stride = stride;
   a.queue = (int*)work;
+  a.G = (const cplx*)G;
+  a.kind = kind;
   a.cap_rows_elems = p.jac_elems;
   a.tpp = p.tpp;
   a.max_sweeps = 60;
@@ -242,6 +251,18 @@ extern "C" int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, i
                                   size_t work_bytes, void* stream) {
   return right_compress_live(in, bonds_in, D_in, out, bonds_out, D_out, D_in, D_out, B, L, max_bond, cutoff, normalize,
                              svals, nsv, amp0, status, work, work_bytes, stream);
+}
+
+extern "C" size_t qsp_apply_inverse_and_compress_workspace_bytes(int B, int L, int D) {
+  return qsp_right_compress_workspace_bytes(B, L, 2 * D, D);
+}
+extern "C" int qsp_apply_inverse_and_compress(const qsp_c128* in, const int32_t* bonds_in, const qsp_c128* G,
+                                              const int32_t* kind, qsp_c128* out, int32_t* bonds_out, int D, int B,
+                                              int L, int max_bond, double cutoff, int normalize, qsp_c128* amp0,
+                                              int32_t* status, void* work, size_t work_bytes, void* stream) {
+  if (!G || !kind) return QSP_ERR_ARG;
+  return right_compress_live(in, bonds_in, D, out, bonds_out, D, 2 * D, D, B, L, max_bond, cutoff, normalize, nullptr, 0,
+                             amp0, status, work, work_bytes, stream, G, kind);
 }
 
 extern "C" int qsp_generate_unitaries(qsp_c128* d2, const int32_t* d2_bonds, int B, int L, qsp_c128* G,
@@ -562,7 +583,7 @@ extern "C" int qsp_encoded_overlap(const qsp_c128* G, const int32_t* kind, int n
 
 struct SeqPlan {
   int De;
-  size_t off_psi, off_psib, off_psi2, off_psi2b, off_d2, off_d2b, off_tmp, off_tmpb;
+  size_t off_psi, off_psib, off_psi2, off_psi2b, off_d2, off_d2b;
   size_t off_enc, off_scratch;
   size_t enc_bytes, scratch_bytes, total;
   bool ok;
@@ -578,14 +599,10 @@ static SeqPlan plan_seq(int B, int L, int D, int layers, int max_bond, int flags
   size_t o = 0;
   p.off_psi = o, o += mps_bytes(B, L, D);
   p.off_psib = o, o += bonds_bytes(B, L);
-  p.off_psi2 = o, o += mps_bytes(B, L, 2 * D);
+  p.off_psi2 = o, o += mps_bytes(B, L, D);  // ping-pong partner of psi (the doubled U^dagger psi is never stored)
   p.off_psi2b = o, o += bonds_bytes(B, L);
   p.off_d2 = o, o += mps_bytes(B, L, 2);
   p.off_d2b = o, o += bonds_bytes(B, L);
-  if (second) {
-    p.off_tmp = o, o += mps_bytes(B, L, D);
-    p.off_tmpb = o, o += bonds_bytes(B, L);
-  }
   size_t s = 0, t;
   DevInfo d = dev_info();
   LCanonPlan lp;
@@ -651,8 +668,6 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
   int32_t* psi2b = (int32_t*)(w + p.off_psi2b);
   qsp_c128* d2 = (qsp_c128*)(w + p.off_d2);
   int32_t* d2b = (int32_t*)(w + p.off_d2b);
-  qsp_c128* tmp = (qsp_c128*)(w + p.off_tmp);
-  int32_t* tmpb = (int32_t*)(w + p.off_tmpb);
   void* encw = w + p.off_enc;
   void* scratch = w + p.off_scratch;
   const size_t sb = p.scratch_bytes;
@@ -672,20 +687,24 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
                                  stream)))
       return rc;
     if ((rc = qsp_generate_unitaries(d2, d2b, B, L, Git, kit, status, stream))) return rc;
-    // apply_inverse_unitary_layer_on_wfn (sequential.py:51) on the left-canonical psi: exact, left canonical
-    if ((rc = qsp_apply_inverse_layer(psi, psib, D, Git, kit, psi2, psi2b, 2 * D, B, L, status, stream))) return rc;
-    // sequential.py:52-57: [right_canonize; compress('right', max_bond)] ; right_canonize(normalize) ; compress()
+    // sequential.py:51-57 in ONE sweep: apply_inverse_unitary_layer_on_wfn on the left-canonical psi (exact,
+    // left canonical, never materialised) fused with [right_canonize; compress('right', max_bond)];
+    // right_canonize(normalize); compress()  -- the fused gate-apply-and-split kernel
     qsp_c128* amp = dis_overlaps + (size_t)it * B;
-    if ((rc = qsp_right_compress(psi2, psi2b, 2 * D, psi, psib, D, B, L, max_bond, cutoff, 1, nullptr, 0,
-                                 second ? nullptr : amp, status, scratch, sb, stream)))
+    if ((rc = right_compress_live(psi, psib, D, psi2, psi2b, D, 2 * D, D, B, L, max_bond, cutoff, 1, nullptr, 0,
+                                  second ? nullptr : amp, status, scratch, sb, stream, Git, kit)))
       return rc;
+    {
+      qsp_c128* t = psi; psi = psi2; psi2 = t;
+      int32_t* tb = psib; psib = psi2b; psi2b = tb;
+    }
     if (second) {
       if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, stream))) return rc;
-      if ((rc = qsp_right_compress(psi, psib, D, tmp, tmpb, D, B, L, 0, cutoff, 1, nullptr, 0, amp, status, scratch,
+      if ((rc = qsp_right_compress(psi, psib, D, psi2, psi2b, D, B, L, 0, cutoff, 1, nullptr, 0, amp, status, scratch,
                                    sb, stream)))
         return rc;
-      dev_copy(psi, tmp, (size_t)B * L * D * 2 * D * sizeof(cplx), st);
-      dev_copy(psib, tmpb, (size_t)B * (L + 1) * sizeof(int32_t), st);
+      qsp_c128* t = psi; psi = psi2; psi2 = t;
+      int32_t* tb = psib; psib = psi2b; psi2b = tb;
     }
     // sequential.py:67-70: encoded state U_0 .. U_it |0..0> and its overlap with the target
     if (enc_on && (it % overlaps_gap == 0 || it + 1 == layers)) {

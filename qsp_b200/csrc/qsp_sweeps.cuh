@@ -299,6 +299,12 @@ struct RCompressArgs {
   cplx* work;               // per-CTA scratch, rcompress_work_elems() each
   long work_stride;         // elements per CTA
   int* queue;               // instance queue head (zeroed before the launch): CTAs pull instances dynamically
+  // Fused gate-apply-and-split (apply_inverse_unitary_layer_on_wfn + compress in one sweep): when G
+  // is set, `in` is the LEFT-canonical chi-MPS psi itself (bonds_in its bonds, Din its padding) and
+  // the sweep runs on U^dagger psi without materialising its doubled tensors:
+  // site t of U^dagger psi is G_{t-1}^dagger o A_{t-1}, so M = A_{t-1} C needs half the flops.
+  const cplx* G;            // [B][L][4][4] or null
+  const int32_t* kind;      // [B][L]
   int cap_rows_elems;       // shared elements available for Jacobi rows
   int tpp;                  // lanes per Jacobi pair
   int max_sweeps;
@@ -363,8 +369,15 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
     int32_t* bo = P.bonds_out + (long)inst * (L + 1);
     int st = 0;
     bool bad = false;
-    for (int i = 0; i <= L; ++i)
-      if (bi[i] > DinL || bi[i] < 1) bad = true;
+    const bool fused = P.G != nullptr;
+    const cplx* Gi = fused ? P.G + (long)inst * L * 16 : nullptr;
+    const int32_t* kd = fused ? P.kind + (long)inst * L : nullptr;
+    for (int i = 0; i <= L; ++i) {
+      // live bond of the swept state: psi itself, or U^dagger psi (doubled inside a segment)
+      int bb = bi[i];
+      if (fused && i > 0 && i < L && kd[i - 1] == 2) bb = 2 * bi[i - 1];
+      if (bb > DinL || bi[i] < 1 || (fused && bi[i] > Din)) bad = true;
+    }
     if (bi[L] > DoutL || bi[0] > DoutL) bad = true;
     if (bad) {
       if (tid == 0 && P.status) P.status[inst] |= QSP_ST_BOND_OVERFLOW;
@@ -383,18 +396,86 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
     for (int i = L - 1; i >= 0; --i) {
       const cplx* Ai = A + (long)i * sin;
       cplx* Oi = O + (long)i * sout;
-      const int b = bi[i], ro = bi[i + 1];  // stored extents of site i
+      // extents of site i of the swept state (left bond b, right bond ro)
+      const bool start = fused && (i == 0 || kd[i - 1] == 1);
+      const int b = (!fused || start) ? bi[i] : 2 * bi[i - 1];
+      const int ro = (!fused || kd[i] == 1) ? bi[i + 1] : 2 * bi[i];
       const int c = 2 * rp;
       QSP_TICK();
-      // ---- M[(x,p),k] = sum_r A[x,p,r] C[r,k]   (C = identity at the last site) -----------
-      if (i == L - 1) {
-        for (int idx = tid; idx < 2 * b * rp; idx += nt) {
-          const int row = idx / rp, k = idx - row * rp;
-          Mg[idx] = Ai[(long)row * Din + k];
+      if (!fused) {
+        // ---- M[(x,p),k] = sum_r A[x,p,r] C[r,k]   (C = identity at the last site) -----------
+        if (i == L - 1) {
+          for (int idx = tid; idx < 2 * b * rp; idx += nt) {
+            const int row = idx / rp, k = idx - row * rp;
+            Mg[idx] = Ai[(long)row * Din + k];
+          }
+          __syncthreads();
+        } else {
+          cta_zgemm_deep(2 * b, rp, ro, Ai, Din, 1, false, Cg, DoutL, 1, false, Mg, rp, 1, false, tiles);
+        }
+      } else if (start && kd[i] == 2) {
+        // first site of a multi-site segment: identity embedding, M[l,(a',k)] = C[(l,a'),k]
+        for (int idx = tid; idx < b * c; idx += nt) {
+          const int l = idx / c, col = idx - l * c;
+          const int ap = col / rp, k = col - ap * rp;
+          Mg[idx] = Cg[((long)l * 2 + ap) * DoutL + k];
         }
         __syncthreads();
       } else {
-        cta_zgemm_deep(2 * b, rp, ro, Ai, Din, 1, false, Cg, DoutL, 1, false, Mg, rp, 1, false, tiles);
+        // T[(x,p),k] = sum_r A_i[x,p,r] C[r,k] is needed for a one-qubit gate on site i
+        // (single-site segment, or the end of a segment); Tg aliases the Jacobi staging area.
+        cplx* Tg = Wg;
+        const cplx* Cuse = Cg;  // carried U s with rows (x,b) [bulk] or r [after a one-qubit gate]
+        long ldC = DoutL;
+        if (kd[i] == 1) {
+          const int xe = bi[i], re = bi[i + 1];
+          if (i == L - 1) {
+            for (int idx = tid; idx < 2 * xe * rp; idx += nt) {
+              const int row = idx / rp, k = idx - row * rp;
+              Tg[idx] = Ai[(long)row * Din + k];
+            }
+            __syncthreads();
+          } else {
+            cta_zgemm_deep(2 * xe, rp, re, Ai, Din, 1, false, Cg, DoutL, 1, false, Tg, rp, 1, false, tiles);
+          }
+          // Q[(x,q),k] = sum_p conj(G_i[p][q]) T[(x,p),k]   (G_i^dagger on the physical leg)
+          const cplx* ge = Gi + i * 16;
+          cplx* Qg = start ? Mg : Vg;  // single-site segment: this already is M
+          for (int idx = tid; idx < 2 * xe * rp; idx += nt) {
+            const int row = idx / rp, k = idx - row * rp;
+            const int x = row >> 1, q = row & 1;
+            cplx acc = cmake(0.0, 0.0);
+            for (int p = 0; p < 2; ++p) cfma_conja(acc, ge[p * 4 + q], Tg[((long)x * 2 + p) * rp + k]);
+            Qg[idx] = acc;
+          }
+          __syncthreads();
+          Cuse = Vg;
+          ldC = rp;
+        }
+        if (!start) {
+          // bulk gate G_{i-1} on (i-1, i):  P[(l,a),(b,k)] = sum_x A_{i-1}[l,a,x] C[(x,b),k],
+          // M[(l,a'),(b',k)] = sum_{a,b} conj(G_{i-1}[(a b)][(a' b')]) P[(l,a),(b,k)]
+          const cplx* Aj = A + (long)(i - 1) * sin;
+          const cplx* g = Gi + (i - 1) * 16;
+          const int lj = bi[i - 1], xj = bi[i];
+          for (int bq = 0; bq < 2; ++bq)
+            cta_zgemm_deep(2 * lj, rp, xj, Aj, Din, 1, false, Cuse + (long)bq * ldC, 2 * ldC, 1, false, Tg + (long)bq * rp,
+                           2L * rp, 1, false, tiles);
+          for (int idx = tid; idx < lj * rp; idx += nt) {
+            const int l = idx / rp, k = idx - l * rp;
+            cplx pv[4];
+#pragma unroll
+            for (int ab = 0; ab < 4; ++ab) pv[ab] = Tg[((long)l * 2 + (ab >> 1)) * (2 * rp) + (ab & 1) * rp + k];
+#pragma unroll
+            for (int apbp = 0; apbp < 4; ++apbp) {
+              cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+              for (int ab = 0; ab < 4; ++ab) cfma_conja(acc, g[ab * 4 + apbp], pv[ab]);
+              Mg[((long)l * 2 + (apbp >> 1)) * c + (apbp & 1) * rp + k] = acc;
+            }
+          }
+          __syncthreads();
+        }
       }
       if (i == 0) {
         // orthogonality centre: site 0 <- M (b x 2 x rp), optional normalisation

@@ -193,6 +193,21 @@ class HostDriver:
         self.sync()
         return out, bo, status
 
+    def apply_inverse_and_compress(self, arr, bonds, G, kind, max_bond=0, cutoff=1e-10, normalize=1):
+        B, L, D = arr.shape[0], arr.shape[1], arr.shape[2]
+        out = self.empty_c(B, L, D, 2, D)
+        bo = self.zeros_i(B, L + 1)
+        status = self.zeros_i(B)
+        amp = self.empty_c(B)
+        wb = self.lib.qsp_apply_inverse_and_compress_workspace_bytes(B, L, D)
+        assert wb > 0, "unsupported size"
+        work = self.work(wb)
+        self.lib.qsp_apply_inverse_and_compress(self.p(arr), self.p(bonds), self.p(G), self.p(kind), self.p(out),
+                                                self.p(bo), D, B, L, max_bond, cutoff, normalize, self.p(amp),
+                                                self.p(status), self.p(work), wb, self.stream)
+        self.sync()
+        return out, bo, status, amp
+
     def overlap(self, a, ba, b, bb):
         B, L, Da, Db = a.shape[0], a.shape[1], a.shape[2], b.shape[2]
         res = self.empty_c(B)

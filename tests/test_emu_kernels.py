@@ -135,6 +135,41 @@ def test_segmented_layer(drv):
     assert abs(O.inner(g, O.apply_unitary_layer_on_wfn(ref, psi)) - 1.0) < 1e-13
 
 
+def test_fused_inverse_and_compress(drv):
+    """qsp_apply_inverse_and_compress == apply_inverse_unitary_layer_on_wfn + right_canonize +
+    compress('right', max_bond) of the reference (core.py:224-240, sequential.py:51-54), segmented layer included."""
+    L = 7
+    psis = [_prepared(O.random_mps(L, 4, 60 + s)) for s in range(2)]
+    layers = [O.generate_bond_d_unitary(p, completion="canonical") for p in psis]
+    # second instance: a hand-made segmented layer (one-site segments and one-qubit segment ends)
+    one = np.zeros((1, 2, 1), complex)
+    one[0, :, 0] = [0.6, 0.8j]
+    bell = np.zeros((1, 2, 2), complex)
+    bell[0, 0, 0], bell[0, 1, 1] = 0.8, 0.6
+    mid = np.zeros((2, 2, 2), complex)
+    mid[0, 0, 0], mid[0, 1, 1], mid[1, 1, 0], mid[1, 0, 1] = 0.6, 0.8, 0.8, -0.6
+    end = np.zeros((2, 2, 1), complex)
+    end[0, 0, 0] = end[1, 1, 0] = 1
+    d2 = [one.copy(), bell.copy(), mid.copy(), end.copy(), one.copy(), bell.copy(), end.copy()]
+    O.right_canonize(d2, normalize=True)
+    layers[1] = O.generate_unitaries(d2, completion="canonical")
+    Gk = [layers_to_gates(l, L) for l in layers]
+    G, kind = np.stack([g for g, _ in Gk]), np.stack([k for _, k in Gk])
+    lc = [O.left_canonize(O.copy_mps(p)) for p in psis]
+    for mb in (0, 4, 3):
+        a, b = pack_batch(lc, 8 if mb == 0 else 4)
+        out, bo, st, amp = drv.apply_inverse_and_compress(a, b, G, kind, max_bond=mb)
+        assert st.max() == 0
+        for k, (p, l, g) in enumerate(zip(psis, layers, unpack_batch(out, bo))):
+            ref = O.apply_inverse_unitary_layer_on_wfn(l, p)
+            O.right_canonize(ref, normalize=True)
+            O.compress(ref, max_bond=mb or None)
+            O.right_canonize(ref, normalize=True)
+            assert O.bonds_of(ref) == O.bonds_of(g), (mb, k)
+            assert abs(O.inner(g, ref) - 1.0) < 1e-12
+            assert abs(amp[k] - O.norm_mps_ovrlap(ref, O.cl_zero_mps(L))) < 1e-12
+
+
 def test_overlap(drv):
     xs = [O.random_mps(6, 3, 1), O.random_mps(6, 3, 2)]
     ys = [O.random_mps(6, 5, 3), O.random_mps(6, 5, 4)]

@@ -140,6 +140,32 @@ def test_apply_layers_match_oracle(drv):
         assert abs(O.inner(g, ref) - 1.0) < 1e-12
 
 
+def test_fused_inverse_and_compress_matches_oracle(drv):
+    """the fused gate-apply-and-split sweep == the reference's inverse staircase + right_canonize +
+    compress('right', max_bond) (core.py:224-240, sequential.py:51-54) as a state, bond profile and amplitude."""
+    from helpers import layers_to_gates
+
+    L, chi = 12, 16
+    psis = [_prepared(O.random_mps(L, chi, 140 + s)) for s in range(3)]
+    layers = [O.generate_bond_d_unitary(p, completion="canonical") for p in psis]
+    Gk = [layers_to_gates(l, L) for l in layers]
+    G = drv.from_host(np.stack([g for g, _ in Gk]))
+    kind = drv.from_host(np.stack([k for _, k in Gk]))
+    lc = [O.left_canonize(O.copy_mps(p)) for p in psis]
+    a, b = _dev(drv, lc, chi)
+    out, bo, st, amp = drv.apply_inverse_and_compress(a, b, G, kind, max_bond=chi)
+    assert drv.to_host(st).max() == 0
+    amp = drv.to_host(amp)
+    for k, (p, l, g) in enumerate(zip(psis, layers, unpack_batch(drv.to_host(out), drv.to_host(bo)))):
+        ref = O.apply_inverse_unitary_layer_on_wfn(l, p)
+        O.right_canonize(ref, normalize=True)
+        O.compress(ref, max_bond=chi)
+        O.right_canonize(ref, normalize=True)
+        assert O.bonds_of(ref) == O.bonds_of(g)
+        assert abs(O.inner(g, ref) - 1.0) < 1e-12
+        assert abs(amp[k] - O.norm_mps_ovrlap(ref, O.cl_zero_mps(L))) < 1e-12
+
+
 def test_overlap_matches_oracle(drv):
     L = 14
     xs = [O.random_mps(L, 6, 50 + s) for s in range(3)]
