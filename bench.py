@@ -397,12 +397,10 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
     d2b = torch.empty((B, L + 1), dtype=torch.int32, device=dev)
     G = torch.empty((B, L, 4, 4), dtype=torch.complex128, device=dev)
     kind = torch.empty((B, L), dtype=torch.int32, device=dev)
-    psi2 = torch.empty((B, L, 2 * chi, 2, 2 * chi), dtype=torch.complex128, device=dev)
-    p2b = torch.empty((B, L + 1), dtype=torch.int32, device=dev)
     out = torch.empty_like(psi)
     ob = torch.empty_like(pb)
     amp = torch.empty(B, dtype=torch.complex128, device=dev)
-    nb = max(lib.qsp_right_compress_workspace_bytes(B, L, chi, 2), lib.qsp_right_compress_workspace_bytes(B, L, 2 * chi, chi))
+    nb = max(lib.qsp_right_compress_workspace_bytes(B, L, chi, 2), lib.qsp_apply_inverse_and_compress_workspace_bytes(B, L, chi))
     work = torch.empty(nb, dtype=torch.uint8, device=dev)
     times = {}
 
@@ -418,12 +416,10 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
     timed("k_right_compress_d2", lambda: lib.qsp_right_compress(p(psi), p(pb), chi, p(d2), p(d2b), 2, B, L, 2, 1e-10, 1,
                                                                  None, 0, None, p(st), p(work), nb, s))
     timed("k_unitaries", lambda: lib.qsp_generate_unitaries(p(d2), p(d2b), B, L, p(G), p(kind), p(st), s))
-    timed("k_expand_inverse", lambda: lib.qsp_apply_inverse_layer(p(psi), p(pb), chi, p(G), p(kind), p(psi2), p(p2b),
-                                                                   2 * chi, B, L, p(st), s))
     reps = []
     for _ in range(2):
-        timed("k_right_compress", lambda: lib.qsp_right_compress(p(psi2), p(p2b), 2 * chi, p(out), p(ob), chi, B, L, chi,
-                                                                  1e-10, 1, None, 0, p(amp), p(st), p(work), nb, s))
+        timed("k_right_compress", lambda: lib.qsp_apply_inverse_and_compress(p(psi), p(pb), p(G), p(kind), p(out), p(ob), chi,
+                                                                              B, L, chi, 1e-10, 1, p(amp), p(st), p(work), nb, s))
         reps.append(times["k_right_compress"])
     dur_ms = float(np.mean(reps))
     fm = flop_model.flops_per_mps(L, chi, 1)
@@ -443,7 +439,7 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
     except Exception:  # noqa: BLE001
         pass
     layer_ms = sum(v for k, v in times.items())
-    return {"bound": "fp64", "kernel": "k_right_compress(2chi->chi)", "achieved": achieved, "peak": peak,
+    return {"bound": "fp64", "kernel": "k_right_compress(fused inverse layer + 2chi->chi)", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
             "note": "achieved counts the REFERENCE's flops this launch replaces (S2+S3+S4 of SURVEY 8d: inverse layer with "
