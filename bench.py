@@ -400,7 +400,8 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
     out = torch.empty_like(psi)
     ob = torch.empty_like(pb)
     amp = torch.empty(B, dtype=torch.complex128, device=dev)
-    nb = max(lib.qsp_right_compress_workspace_bytes(B, L, chi, 2), lib.qsp_apply_inverse_and_compress_workspace_bytes(B, L, chi))
+    nb = max(lib.qsp_right_compress_workspace_bytes(B, L, chi, 2), lib.qsp_apply_inverse_and_compress_workspace_bytes(B, L, chi),
+             lib.qsp_left_canonize_workspace_bytes(B, L, chi))
     work = torch.empty(nb, dtype=torch.uint8, device=dev)
     times = {}
 
@@ -412,7 +413,7 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
         torch.cuda.synchronize()
         times[name] = e0.elapsed_time(e1)
 
-    timed("k_left_canon", lambda: lib.qsp_left_canonize(p(psi), p(pb), B, L, chi, p(st), s))
+    timed("k_left_canon", lambda: lib.qsp_left_canonize(p(psi), p(pb), B, L, chi, p(st), p(work), nb, s))
     timed("k_right_compress_d2", lambda: lib.qsp_right_compress(p(psi), p(pb), chi, p(d2), p(d2b), 2, B, L, 2, 1e-10, 1,
                                                                  None, 0, None, p(st), p(work), nb, s))
     timed("k_unitaries", lambda: lib.qsp_generate_unitaries(p(d2), p(d2b), B, L, p(G), p(kind), p(st), s))

@@ -59,8 +59,12 @@ const char* qsp_last_cuda_error(void);
 long long qsp_launch_count(void);
 
 /* quimb MPS.left_canonize() in place (first half of `compress`, tsp.py:72, core.py:17,
- * sequential.py:54,57).  R has a non-negative real diagonal (quimb's stabilised QR). */
-int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* stream);
+ * sequential.py:54,57).  R has a non-negative real diagonal (quimb's stabilised QR).
+ * Bonds whose (2D x D) site matrix fits shared memory (D <= ~85) need no workspace (the query
+ * returns 0, work may be NULL); larger bonds (D <= 256) run out of an L2-resident scratch. */
+size_t qsp_left_canonize_workspace_bytes(int B, int L, int D);
+int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* work,
+                      size_t work_bytes, void* stream);
 
 /* quimb MPS.right_compress(max_bond, cutoff, cutoff_mode='rel') on a LEFT-canonical input:
  * right-to-left truncating SVD sweep (second half of `compress`).  max_bond = 0: cutoff
@@ -157,6 +161,7 @@ void qsp_set_profile_buffer(void* buf);
 int qsp_jacobi_bench_fat(qsp_c128* W, int nrows, int ldw, int B, int* sweeps, int* ok, void* stream);
 int qsp_smem_probe(double* out, int blocks, int iters, int mode, void* stream); /* shared-memory bandwidth probe */
 void qsp_jacobi_variant(int bits); /* timing experiments: disables parts of the Jacobi round (results invalid) */
+void qsp_debug_flags(int flags);    /* test hook: bit 0 = take the large-bond left-canonise path at any size */
 int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int nt, int* sweeps, int* ok, void* stream);
 
 /* Measurement aid: blocks x threads threads each run `iters` rounds of 16 independent

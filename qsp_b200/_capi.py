@@ -21,7 +21,9 @@ _SIGNATURES = {
     "qsp_is_device_build": (_i, []),
     "qsp_last_cuda_error": (C.c_char_p, []),
     "qsp_launch_count": (C.c_longlong, []),
-    "qsp_left_canonize": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "qsp_left_canonize_workspace_bytes": (_sz, [_i, _i, _i]),
+    "qsp_left_canonize": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, _p]),
+    "qsp_debug_flags": (None, [_i]),
     "qsp_right_compress_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "qsp_right_compress": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _d, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "qsp_generate_unitaries": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),

@@ -97,16 +97,29 @@ static int grid_for(int B, int per_sm, const DevInfo& d) {
 struct LCanonPlan {
   int nt;
   size_t smem;
+  bool big;  // site matrix in the L2-resident scratch (k_left_canon_big)
 };
+static int g_force_big = 0;  // test hook (qsp_debug_flags bit 0): take the large-bond path at any size
 static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
-  if (2 * D > 32 * QSP_QR_MAXR) return false;  // a column must fit one warp's registers
-  p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : (D <= 48 ? 256 : 512));
-  p->smem = lcanon_smem_bytes(D, p->nt);
-  if (p->smem > d.max_smem && p->nt == 512) {
-    p->nt = 256;
+  p->big = false;
+  if (2 * D <= 32 * QSP_QR_MAXR && !g_force_big) {  // a column must fit one warp's registers
+    p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : (D <= 48 ? 256 : 512));
     p->smem = lcanon_smem_bytes(D, p->nt);
+    if (p->smem > d.max_smem && p->nt == 512) {
+      p->nt = 256;
+      p->smem = lcanon_smem_bytes(D, p->nt);
+    }
+    if (p->smem <= d.max_smem) return true;
   }
+  if (2 * D > 32 * QSP_QR_MAXR_BIG) return false;
+  p->big = true;
+  p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : 256);
+  p->smem = lcanon_smem_bytes_big(D, p->nt);
   return p->smem <= d.max_smem;
+}
+static int lcanon_grid(int B, const LCanonPlan& p, const DevInfo& d) {
+  const void* k = p.big ? (const void*)k_left_canon_big : (const void*)k_left_canon;
+  return grid_for(B, blocks_per_sm(k, p.nt, p.smem), d);
 }
 
 struct RCompressPlan {
@@ -158,22 +171,42 @@ extern "C" long long qsp_launch_count(void) { return g_launches; }
 
 // Dlive: largest bond that can occur in this call (<= D, the padded stride); the launch (threads,
 // shared memory, CTAs per SM) is planned for Dlive, a larger live bond sets QSP_ST_BOND_OVERFLOW.
+extern "C" size_t qsp_left_canonize_workspace_bytes(int B, int L, int D) {
+  (void)L;
+  DevInfo d = dev_info();
+  LCanonPlan p;
+  if (B <= 0 || D <= 0 || !plan_lcanon(D, d, &p) || !p.big) return 0;
+#ifndef QSP_EMU
+  QSP_PREP_KERNEL(k_left_canon_big, p.smem);
+#endif
+  return align_up((size_t)lcanon_grid(B, p, d) * lcanon_work_elems(D) * sizeof(cplx));
+}
 static int left_canonize_live(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int Dlive, int32_t* status,
-                              void* stream) {
+                              void* work, size_t work_bytes, void* stream) {
   if (!mps || !bonds || B <= 0 || L <= 0 || D <= 0) return QSP_ERR_ARG;
   if (Dlive > D || Dlive <= 0) Dlive = D;
   DevInfo d = dev_info();
   LCanonPlan p;
   if (!plan_lcanon(Dlive, d, &p)) return QSP_ERR_UNSUPPORTED;
-  QSP_PREP_KERNEL(k_left_canon, p.smem);
-  int grid = grid_for(B, blocks_per_sm((const void*)k_left_canon, p.nt, p.smem), d);
-  QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, Dlive, status, g_prof);
+  if (p.big) {
+    QSP_PREP_KERNEL(k_left_canon_big, p.smem);
+    int grid = lcanon_grid(B, p, d);
+    if (!work || work_bytes < (size_t)grid * lcanon_work_elems(Dlive) * sizeof(cplx)) return QSP_ERR_WORKSPACE;
+    QSP_LAUNCH(k_left_canon_big, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, Dlive, status,
+               g_prof, (cplx*)work);
+  } else {
+    QSP_PREP_KERNEL(k_left_canon, p.smem);
+    int grid = lcanon_grid(B, p, d);
+    QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, Dlive, status, g_prof);
+  }
   ++g_launches;
   return check_launch();
 }
-extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* stream) {
-  return left_canonize_live(mps, bonds, B, L, D, D, status, stream);
+extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* work,
+                                 size_t work_bytes, void* stream) {
+  return left_canonize_live(mps, bonds, B, L, D, D, status, work, work_bytes, stream);
 }
+extern "C" void qsp_debug_flags(int flags) { g_force_big = flags & 1; }
 
 static int rcompress_grid(int B, const RCompressPlan& p, const DevInfo& d) {
   return grid_for(B, blocks_per_sm((const void*)k_right_compress, p.nt, p.smem), d);
@@ -466,8 +499,18 @@ extern "C" int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int 
 static size_t mps_bytes(int B, int L, int D) { return align_up((size_t)B * L * D * 2 * D * sizeof(cplx)); }
 static size_t bonds_bytes(int B, int L) { return align_up((size_t)B * (L + 1) * sizeof(int32_t)); }
 
+// scratch shared by the left sweep (large bonds only) and the right sweep of a compress at bond D
+static size_t compress_scratch_bytes(int B, int L, int D_in, int D_out) {
+  DevInfo d = dev_info();
+  LCanonPlan lp;
+  if (!plan_lcanon(D_in, d, &lp)) return 0;
+  size_t w = qsp_right_compress_workspace_bytes(B, L, D_in, D_out);
+  if (w == 0) return 0;
+  size_t l = qsp_left_canonize_workspace_bytes(B, L, D_in);
+  return w > l ? w : l;
+}
 extern "C" size_t qsp_prepare_target_workspace_bytes(int B, int L, int D) {
-  size_t w = qsp_right_compress_workspace_bytes(B, L, D, D);
+  size_t w = compress_scratch_bytes(B, L, D, D);
   if (w == 0) return 0;
   return mps_bytes(B, L, D) + bonds_bytes(B, L) + w;
 }
@@ -482,8 +525,8 @@ extern "C" int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, i
   w += mps_bytes(B, L, D);
   int32_t* tb = (int32_t*)w;
   w += bonds_bytes(B, L);
-  size_t wb = qsp_right_compress_workspace_bytes(B, L, D, D);
-  int rc = qsp_left_canonize(mps, bonds, B, L, D, status, stream);
+  size_t wb = compress_scratch_bytes(B, L, D, D);
+  int rc = qsp_left_canonize(mps, bonds, B, L, D, status, w, wb, stream);
   if (rc) return rc;
   rc = qsp_right_compress(mps, bonds, D, tmp, tb, D, B, L, 0, cutoff, 1, nullptr, 0, nullptr, status, w, wb, stream);
   if (rc) return rc;
@@ -500,7 +543,7 @@ extern "C" int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, i
 // compress('right') after each layer (core.py:140, cutoff only) changes nothing but the bond
 // sizes.  Mode A (layers <= 8): buffers of 2^layers, no compression at all.  Mode B (more layers,
 // short chains with 2^(L/2+1) <= 64): 64-padded buffers, compress whenever the next doubling would
-// not fit (true rank <= 2^(L/2)).
+// not fit (true rank <= 2^(L/2)); chains of 12..15 sites the same way with 256-padded buffers.
 struct EncPlan {
   int De;        // padded bond of both encoded-state buffers
   bool compress; // mode B
@@ -512,8 +555,8 @@ static EncPlan plan_enc(int L, int layers) {
   e.compress = false;
   if (layers <= 8) {
     e.De = 1 << layers;
-  } else if (L / 2 + 1 <= 6) {
-    e.De = 64;
+  } else if (L / 2 + 1 <= 8) {
+    e.De = (L / 2 + 1 <= 6) ? 64 : 256;
     e.compress = true;
   } else {
     e.De = 1;
@@ -526,7 +569,7 @@ extern "C" size_t qsp_encoded_overlap_workspace_bytes(int B, int L, int D, int l
   if (!e.ok) return 0;
   size_t s = qsp_overlap_workspace_bytes(B, L, e.De, D);
   if (e.compress) {
-    size_t t = qsp_right_compress_workspace_bytes(B, L, e.De, e.De);
+    size_t t = compress_scratch_bytes(B, L, e.De, e.De);
     if (!t) return 0;
     s = t > s ? t : s;
   }
@@ -562,7 +605,7 @@ extern "C" int qsp_encoded_overlap(const qsp_c128* G, const int32_t* kind, int n
   const int rank_cap = 1 << imin(L / 2, 20);
   for (int k = n - 1; k >= 0; --k) {
     if (2 * cur > De) {  // mode B: bring the bonds back to the true rank before doubling them again
-      if ((rc = left_canonize_live(ea, eab, B, L, De, cur, status, stream))) return rc;
+      if ((rc = left_canonize_live(ea, eab, B, L, De, cur, status, w, sb, stream))) return rc;
       if ((rc = right_compress_live(ea, eab, De, eb, ebb, De, cur, imin(cur, rank_cap), B, L, 0, cutoff, 0, nullptr, 0,
                                     nullptr, status, w, sb, stream)))
         return rc;
@@ -607,6 +650,7 @@ static SeqPlan plan_seq(int B, int L, int D, int layers, int max_bond, int flags
   DevInfo d = dev_info();
   LCanonPlan lp;
   if (!plan_lcanon(D, d, &lp)) p.ok = false;
+  s = qsp_left_canonize_workspace_bytes(B, L, D);
   t = qsp_right_compress_workspace_bytes(B, L, D, 2);
   if (!t) p.ok = false;
   s = t > s ? t : s;
@@ -682,7 +726,7 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
     int32_t* kit = kind + (size_t)it * B * L;
     double* sv = d2_svals ? d2_svals + (size_t)it * B * (L - 1) * 2 : nullptr;
     // generate_bond_d_unitary (core.py:12-22): compress('right', max_bond=2) = left sweep + truncating right sweep
-    if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, stream))) return rc;
+    if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, scratch, sb, stream))) return rc;
     if ((rc = qsp_right_compress(psi, psib, D, d2, d2b, 2, B, L, 2, cutoff, 1, sv, 2, nullptr, status, scratch, sb,
                                  stream)))
       return rc;
@@ -699,7 +743,7 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
       int32_t* tb = psib; psib = psi2b; psi2b = tb;
     }
     if (second) {
-      if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, stream))) return rc;
+      if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, scratch, sb, stream))) return rc;
       if ((rc = qsp_right_compress(psi, psib, D, psi2, psi2b, D, B, L, 0, cutoff, 1, nullptr, 0, amp, status, scratch,
                                    sb, stream)))
         return rc;

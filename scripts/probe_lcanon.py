@@ -16,7 +16,7 @@ for rep in range(2):
     prof = torch.zeros((4096, 8), dtype=torch.int64, device=dev)
     eng.lib.qsp_set_profile_buffer(p(prof))
     torch.cuda.synchronize(); t0 = time.time()
-    eng.lib.qsp_left_canonize(p(x), p(xb), B, L, chi, p(st), s)
+    eng.lib.qsp_left_canonize(p(x), p(xb), B, L, chi, p(st), None, 0, s)
     torch.cuda.synchronize(); dt = time.time() - t0
     eng.lib.qsp_set_profile_buffer(None)
     pr = prof.cpu().numpy().astype(float); pr = pr[pr[:, 6] > 0]

@@ -152,7 +152,9 @@ class HostDriver:
     def left_canonize(self, arr, bonds):
         B, L, D = arr.shape[0], arr.shape[1], arr.shape[2]
         status = self.zeros_i(B)
-        self.lib.qsp_left_canonize(self.p(arr), self.p(bonds), B, L, D, self.p(status), self.stream)
+        wb = self.lib.qsp_left_canonize_workspace_bytes(B, L, D)
+        work = self.work(wb) if wb else None
+        self.lib.qsp_left_canonize(self.p(arr), self.p(bonds), B, L, D, self.p(status), self.p(work), wb, self.stream)
         self.sync()
         return status
 

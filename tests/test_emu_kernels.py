@@ -36,6 +36,25 @@ def test_left_canonize(drv):
         assert max(np.abs(x - y).max() for x, y in zip(ref, g)) < 1e-13
 
 
+@pytest.fixture
+def big_path(drv):
+    """qsp_debug_flags bit 0: left-canonise out of the L2 scratch (the chi > 85 path) at any size"""
+    drv.lib.qsp_debug_flags(1)
+    yield drv
+    drv.lib.qsp_debug_flags(0)
+
+
+def test_large_bond_left_canonize_path(big_path):
+    drv = big_path
+    assert drv.lib.qsp_left_canonize_workspace_bytes(2, 7, 6) > 0
+    test_left_canonize(drv)
+    test_prepare_target(drv)
+    test_layer_loop(drv, "compressed")
+    test_layer_loop(drv, "ten_layers_short_chain")
+    assert drv.lib._qsp_left_canonize(drv.p(np.zeros(4 * 2 * 4 * 4, np.complex128)), drv.p(np.ones(5, np.int32)), 1, 4, 4,
+                                      None, None, 0, None) == 3  # QSP_ERR_WORKSPACE
+
+
 @pytest.mark.parametrize("max_bond", [0, 3, 2])
 def test_right_compress(drv, max_bond):
     mpss = []
@@ -235,7 +254,7 @@ def test_status_bits_and_error_codes(drv):
     assert r["status"][0] & 2
     # unsupported size is reported before anything is launched
     assert drv.lib.qsp_seq_prepare_workspace_bytes(1, 10, 512, 2, 512, 0) == 0
-    assert drv.lib._qsp_left_canonize(None, None, 1, 4, 4, None, None) == 1
+    assert drv.lib._qsp_left_canonize(None, None, 1, 4, 4, None, None, 0, None) == 1
 
 
 @pytest.mark.parametrize("name", list(edge_cases()))

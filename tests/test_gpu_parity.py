@@ -46,7 +46,7 @@ def _dev(drv, mps_list, D=None):
 # ---------------------------------------------------------------------------------------
 # unit level
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("L,chi", [(6, 4), (12, 16), (20, 64), (9, 5)])
+@pytest.mark.parametrize("L,chi", [(6, 4), (12, 16), (20, 64), (9, 5), (16, 100), (18, 256)])
 def test_left_canonize_matches_oracle(drv, L, chi):
     mpss = [O.random_mps(L, chi, 10 + s) for s in range(3)]
     for m in mpss:  # keep entries O(1)
@@ -233,6 +233,23 @@ def test_pipeline_chi64(drv):
     """headline bond dimension on a short chain (the oracle needs seconds per instance)."""
     tg = [_prepared(O.random_mps(16, 64, 90 + s)) for s in range(2)]
     _check_pipeline(drv, tg, 2, 64, 64)
+
+
+@pytest.mark.parametrize("L,chi,layers,no_comp", [(16, 128, 2, False), (18, 256, 1, False), (14, 32, 2, True)])
+def test_pipeline_large_bonds(drv, L, chi, layers, no_comp):
+    """bonds beyond what fits shared memory (BASELINE configs[4] has chi = 256): the sweeps run out of the
+    L2-resident scratch.  no_comp: bonds double per layer without compression (32 -> 128, capped at 2^(L/2))."""
+    tg = [_prepared(O.random_mps(L, chi, 95 + s)) for s in range(2)]
+    if no_comp:
+        _check_pipeline(drv, tg, layers, 0, min(chi * 2 ** layers, 2 ** (L // 2)))
+    else:
+        _check_pipeline(drv, tg, layers, chi, chi)
+
+
+def test_pipeline_ten_layers_on_14_sites(drv):
+    """more than 8 layers: the encoded state (exact bond 2^layers) is re-compressed between layers (256-padded buffers)."""
+    tg = [_prepared(O.random_mps(14, 8, 97 + s)) for s in range(2)]
+    _check_pipeline(drv, tg, 10, 8, 8, check_svals=False)
 
 
 @pytest.mark.parametrize("name", list(edge_cases()))
