@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_HERE, "libqsp_b200.so")
+DEFAULT_LIB = os.environ.get("QSP_B200_LIB") or os.path.join(_HERE, "libqsp_b200.so")
 
 ST_JACOBI_NOCONV, ST_BOND_OVERFLOW, ST_NONUNITARY, ST_DEGENERATE, ST_BADNORM = 1, 2, 4, 8, 16
 FLAG_SECOND_PASS, FLAG_NO_ENCODED = 1, 2

@@ -1,6 +1,7 @@
-set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/gpu_tests.log 2>&1; echo "tests rc=$?"
-tail -15 gpurun_out/gpu_tests.log
-timeout 300 python scripts/probe.py 24 128 1 148 1 > gpurun_out/probe128.log 2>&1; tail -3 gpurun_out/probe128.log
-timeout 300 python scripts/probe.py 20 256 1 32 1 > gpurun_out/probe256.log 2>&1; tail -3 gpurun_out/probe256.log
+for lib in "" scripts/_alt/libqsp_nonc.so; do
+  echo "== lib=${lib:-default(norm cache)}"
+  QSP_B200_LIB=$lib timeout 200 python scripts/jacobi_bench.py 128 128 512 592 2>&1 | tail -1
+  QSP_B200_LIB=$lib timeout 200 python scripts/jacobi_bench.py 64 128 512 592 2>&1 | tail -1
+  QSP_B200_LIB=$lib PROBE_PROF=1 PROBE_ENC=0 timeout 300 python scripts/probe.py 100 64 1 592 2 2>&1 | tail -3
+done

@@ -93,6 +93,39 @@ def test_block_jacobi_path(drv):
     assert abs(O.inner(g, ref) - 1.0) < 1e-12
 
 
+def _jacobi_cases(nrows, ncols, seed=3):
+    rng = np.random.default_rng(seed)
+    g = lambda *sh: rng.standard_normal(sh) + 1j * rng.standard_normal(sh)
+    full = g(nrows, ncols)
+    low = g(nrows, 3) @ g(3, ncols)                          # rank 3: most rows collapse to roundoff
+    graded = g(nrows, ncols) * np.logspace(0, -9, ncols)     # graded columns (the carried U s)
+    dup = full.copy(); dup[1] = dup[0]; dup[5] = 2 * dup[4]  # exactly dependent rows
+    zero = full.copy(); zero[2] = 0                          # a zero row
+    return {"full": full, "rank3": low, "graded": graded, "duplicates": dup, "zero_row": zero}
+
+
+@pytest.mark.parametrize("nrows,ldw,nt", [(16, 128, 64), (15, 128, 64), (8, 64, 64)])
+def test_jacobi_register_variants(drv, nrows, ldw, nt):
+    """the register-resident odd-even Jacobi on its own: (16,128,64) is the 16-columns-per-lane geometry of the
+    headline shape (plain rotations, carried row norms); singular values to 1e-12, rows orthogonal."""
+    cases = _jacobi_cases(nrows, ldw)
+    W = np.ascontiguousarray(np.stack(list(cases.values())))
+    B = W.shape[0]
+    ref = W.copy()
+    sw, ok = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    assert drv.lib._qsp_jacobi_bench(drv.p(W), nrows, ldw, ldw, B, nt, drv.p(sw), drv.p(ok), None) == 0
+    assert ok.min() == 1, (ok, sw)
+    for k, name in enumerate(cases):
+        s_ref = np.linalg.svd(ref[k], compute_uv=False)
+        s = np.sort(np.linalg.norm(W[k], axis=1))[::-1]
+        assert np.allclose(s, s_ref, rtol=1e-12, atol=1e-13 * s_ref[0]), name
+        keep = np.linalg.norm(W[k], axis=1) > 1e-8 * s_ref[0]
+        V = W[k][keep] / np.linalg.norm(W[k][keep], axis=1)[:, None]
+        assert np.abs(V @ V.conj().T - np.eye(keep.sum())).max() < 1e-13, name
+        # the rotations are unitary: the row space (Gram matrix of columns) is unchanged
+        assert np.abs(W[k].conj().T @ W[k] - ref[k].conj().T @ ref[k]).max() < 1e-12 * s_ref[0] ** 2, name
+
+
 def test_unitaries_and_layers(drv):
     L = 8
     tg = [_prepared(O.random_mps(L, 4, 20 + s)) for s in range(2)]
