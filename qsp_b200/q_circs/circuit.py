@@ -1,9 +1,13 @@
 """Circuit emission (qsp/q_circs/qiskit_circuit.py:34-70).  The circuit object is
 assembled in Python, as in the reference.  With qiskit installed the reference's own
-construction is used (circ.unitary + transpile to {cx, u3}); without it a plain gate list
-with the same ordering / endianness and the accessors the facade reads (tsp.py:146) stands
-in.  The L <= 16 statevector cross-check (qiskit_circuit.py:52-67) runs on the GPU."""
+construction is used (circ.unitary + transpile to {cx, u3}); without it the gate list (same
+ordering / endianness) is synthesised into {cx, u3} here (kak.py: three CNOTs per generic
+two-qubit unitary, adjacent one-qubit gates merged) and wrapped in a small circuit class with
+the accessors the facade reads (tsp.py:146).  The statevector cross-check
+(qiskit_circuit.py:52-67) runs on the GPU, on the synthesised {cx, u3} circuit."""
 import numpy as np
+
+from . import kak
 
 try:  # pragma: no cover - qiskit is not in the build image
     import qiskit
@@ -64,6 +68,100 @@ class GateListCircuit:
         return psi
 
 
+class CxU3Circuit:
+    """{cx, u3} circuit: what `qiskit.transpile(circ, basis_gates=["cx", "u3"])` returns in the
+    reference (qiskit_circuit.py:50).  gates: ("u3", [q], (theta, phi, lam)) / ("cx", [control, target], ())
+    in application order; global_phase is kept so that the circuit equals the unitary list exactly."""
+
+    def __init__(self, num_qubits):
+        self.num_qubits = num_qubits
+        self.gates = []
+        self.global_phase = 0.0
+        self.source = None  # the GateListCircuit it was synthesised from
+
+    @classmethod
+    def from_gate_list(cls, gl, atol=1e-10):
+        """Synthesis + one-qubit merging: a pending 2x2 product per qubit is flushed as ONE u3 when a cx
+        touches the qubit (or at the end); products that are a phase times the identity are dropped."""
+        self = cls(gl.num_qubits)
+        self.source = gl
+        pending = [None] * gl.num_qubits
+        rng = np.random.default_rng(7)
+
+        def push(q, m):
+            pending[q] = m if pending[q] is None else m @ pending[q]
+
+        def flush(q):
+            m, pending[q] = pending[q], None
+            if m is None:
+                return
+            th, ph, la, ga = kak.u3_params(m)
+            self.global_phase += ga
+            if np.abs(kak.u3_matrix(th, ph, la) - np.eye(2)).max() > atol:
+                self.gates.append(("u3", [q], (th, ph, la)))
+
+        for u, qs in gl.gates:
+            if len(qs) == 1:
+                push(qs[0], u)
+                continue
+            # matrix index = 2 * bit(qs[1]) + bit(qs[0]): left factor <-> qs[1], right factor <-> qs[0]
+            side = (qs[1], qs[0])
+            phase, ops = kak.decompose_two_qubit(u, rng)
+            self.global_phase += float(np.angle(phase))
+            for op in ops:
+                if op[0] == "u":
+                    push(side[op[1]], op[2])
+                else:
+                    c, t = side[op[1]], side[op[2]]
+                    flush(c)
+                    flush(t)
+                    self.gates.append(("cx", [c, t], ()))
+        for q in range(gl.num_qubits):
+            flush(q)
+        return self
+
+    def size(self):
+        return len(self.gates)
+
+    def num_nonlocal_gates(self):
+        return sum(1 for g in self.gates if g[0] == "cx")
+
+    def count_ops(self):
+        n2 = self.num_nonlocal_gates()
+        return {"u3": self.size() - n2, "cx": n2}
+
+    def depth(self):
+        busy = [0] * self.num_qubits
+        for _, q, _ in self.gates:
+            d = max(busy[i] for i in q) + 1
+            for i in q:
+                busy[i] = d
+        return max(busy) if busy else 0
+
+    def as_gate_list(self):
+        """The same circuit as explicit matrices (GateListCircuit), global phase folded into the first gate."""
+        gl = GateListCircuit(self.num_qubits)
+        cx = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128)  # [control, target]
+        for name, q, par in self.gates:
+            gl.unitary(kak.u3_matrix(*par) if name == "u3" else cx, q)
+        if gl.gates:
+            gl.gates[0] = (gl.gates[0][0] * np.exp(1j * self.global_phase), gl.gates[0][1])
+        return gl
+
+    def statevector(self, device="cuda:0"):
+        return self.as_gate_list().statevector(device)
+
+    def qasm(self):
+        """OpenQASM 2 text of the circuit (global phase dropped, as OpenQASM 2 has none)."""
+        out = ["OPENQASM 2.0;", 'include "qelib1.inc";', f"qreg q[{self.num_qubits}];"]
+        for name, q, par in self.gates:
+            if name == "u3":
+                out.append("u3(%.17g,%.17g,%.17g) q[%d];" % (par[0], par[1], par[2], q[0]))
+            else:
+                out.append("cx q[%d],q[%d];" % (q[0], q[1]))
+        return "\n".join(out) + "\n"
+
+
 def _dense_from_mps(arrays, device):
     import torch
 
@@ -91,7 +189,7 @@ def circuit_from_unitary_layers(unitary_layers, L, target_mps=None, device="cuda
     if use_qiskit:  # pragma: no cover
         circ = qiskit.transpile(circ, basis_gates=["cx", "u3"])
     else:
-        shadow = circ
+        circ = shadow = CxU3Circuit.from_gate_list(circ)
     overlap_from_seq_circ = None
     arrays = getattr(target_mps, "arrays", None)
     if L <= 16 and arrays is not None:

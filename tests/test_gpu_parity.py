@@ -325,7 +325,12 @@ def test_facade_readme_example(drv, capsys):
     psi = O.circuit_statevector(layers, 10)
     dense = O.mps_to_dense(ref["mps_orig"])
     assert abs(abs(np.vdot(dense, psi)) - abs(overlap)) < 1e-10
-    assert circ.size() == sum(ref["gate_counts"][-1:]) and circ.num_nonlocal_gates() > 0
+    # circ is the {cx, u3} circuit (qiskit_circuit.py:50); its source gate list has the reference's gate count
+    assert circ.source.size() == sum(ref["gate_counts"][-1:])
+    assert circ.num_nonlocal_gates() == 3 * circ.source.num_nonlocal_gates()
+    assert set(circ.count_ops()) == {"u3", "cx"} and circ.size() == sum(circ.count_ops().values())
+    sv = circ.statevector().reshape(-1).cpu().numpy()  # axis i = qubit i, same as the oracle's dense vector
+    assert abs(abs(np.vdot(dense, sv)) - abs(overlap)) < 1e-10
     out = capsys.readouterr().out
     assert "preparing mps using sequential unitaries (num_seq_layers=4)" in out
 

@@ -1,0 +1,101 @@
+"""{cx, u3} synthesis (qsp_b200/q_circs/kak.py) -- the stand-in for the reference's
+qiskit.transpile(circ, basis_gates=["cx", "u3"]) (qiskit_circuit.py:50): every emitted circuit must
+equal the unitary list it came from, exactly (global phase included)."""
+import numpy as np
+import pytest
+from scipy.stats import unitary_group
+
+from qsp_b200.q_circs import kak
+from qsp_b200.q_circs.circuit import CxU3Circuit, GateListCircuit
+
+CX = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=complex)
+SWAP = np.eye(4)[[0, 2, 1, 3]].astype(complex)
+
+
+def _specials():
+    u2 = lambda s: unitary_group.rvs(2, random_state=s)
+    return {
+        "identity": np.eye(4, dtype=complex),
+        "cx": CX,
+        "xc": SWAP @ CX @ SWAP,
+        "cz": np.diag([1, 1, 1, -1]).astype(complex),
+        "swap": SWAP,
+        "product": np.kron(u2(1), u2(2)),
+        "cphase": np.diag(np.exp(1j * np.array([0, 0, 0, 0.3]))),
+        "swap_cx": SWAP @ CX,
+        "sqrt_swap": np.array([[1, 0, 0, 0], [0, (1 + 1j) / 2, (1 - 1j) / 2, 0], [0, (1 - 1j) / 2, (1 + 1j) / 2, 0], [0, 0, 0, 1]]),
+        "real_orthogonal": np.linalg.qr(np.random.default_rng(3).standard_normal((4, 4)))[0].astype(complex),
+        "phase_times_identity": np.exp(0.7j) * np.eye(4),
+    }
+
+
+@pytest.mark.parametrize("name", list(_specials()))
+def test_special_two_qubit_gates(name):
+    u = _specials()[name]
+    ph, ops = kak.decompose_two_qubit(u)
+    assert np.abs(ph * kak.ops_to_matrix(ops) - u).max() < 1e-10
+    ncx = sum(1 for o in ops if o[0] == "cx")
+    assert ncx == (0 if name in ("identity", "product", "phase_times_identity") else 3)
+
+
+def test_random_two_qubit_gates():
+    worst = 0.0
+    for s in range(300):
+        u = unitary_group.rvs(4, random_state=s)
+        ph, ops = kak.decompose_two_qubit(u)
+        worst = max(worst, np.abs(ph * kak.ops_to_matrix(ops) - u).max())
+    assert worst < 1e-11
+
+
+def test_weyl_coordinates_of_canonical_gate():
+    from scipy.linalg import expm
+
+    X, Y, Z = np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1.0, -1.0])
+    a, b, c = 0.31, -0.17, 0.05
+    n = expm(1j * (a * np.kron(X, X) + b * np.kron(Y, Y) + c * np.kron(Z, Z)))
+    w, _ = kak.three_cx_core(*kak.weyl_coordinates(n))
+    ph, ops = kak.decompose_two_qubit(n)
+    assert np.abs(ph * kak.ops_to_matrix(ops) - n).max() < 1e-11
+    # the three-CNOT core has the same local invariants (spectrum of m^T m in the magic basis, up to sign)
+    spec = lambda m: np.sort_complex(np.round(np.linalg.eigvals((lambda p: p.T @ p)(kak._MAGIC.conj().T @ kak._su4(m)[0] @ kak._MAGIC)) ** 2, 9))
+    assert np.allclose(spec(w), spec(n), atol=1e-7)
+
+
+def test_u3_params_round_trip():
+    mats = [unitary_group.rvs(2, random_state=s) for s in range(50)]
+    mats += [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1, 1j]), np.exp(0.4j) * np.array([[0, -1], [1, 0]])]
+    for m in mats:
+        th, ph, la, ga = kak.u3_params(m)
+        assert np.abs(np.exp(1j * ga) * kak.u3_matrix(th, ph, la) - m).max() < 1e-12
+
+
+def test_circuit_synthesis_equals_gate_list():
+    """a sequential-circuit shaped gate list (staircases of [it+1, it] gates closed by a one-qubit gate)"""
+    L = 6
+    gl = GateListCircuit(L)
+    s = 0
+    for layer in range(3):
+        for it in range(L - 1):
+            gl.unitary(unitary_group.rvs(4, random_state=s), [it + 1, it]); s += 1
+        gl.unitary(unitary_group.rvs(2, random_state=s), [L - 1]); s += 1
+    circ = CxU3Circuit.from_gate_list(gl)
+    a = gl.statevector("cpu").reshape(-1)
+    b = circ.statevector("cpu").reshape(-1)
+    assert float(abs(a - b).max()) < 1e-11                      # exact, global phase included
+    n2 = gl.num_nonlocal_gates()
+    assert circ.num_nonlocal_gates() == 3 * n2
+    assert circ.count_ops() == {"u3": circ.size() - 3 * n2, "cx": 3 * n2}
+    # merging: one u3 per qubit in front of a block, two after its first cx, one after its second ->
+    # at most 5 per block plus the trailing flush (an unmerged synthesis has 8 per block)
+    assert circ.size() - 3 * n2 <= 5 * n2 + L
+    assert circ.depth() >= 3 * (L - 1)
+    q = circ.qasm()
+    assert q.count("cx q[") == 3 * n2 and q.startswith("OPENQASM 2.0;")
+
+
+def test_identity_gates_are_dropped():
+    gl = GateListCircuit(3)
+    gl.unitary(np.eye(4), [1, 0])
+    gl.unitary(np.exp(0.3j) * np.eye(2), [2])
+    circ = CxU3Circuit.from_gate_list(gl)
+    assert circ.size() == 0 and abs(np.exp(1j * circ.global_phase) - np.exp(0.3j)) < 1e-12
