@@ -14,8 +14,12 @@
 #pragma once
 #include "qsp_common.cuh"
 
+// A sweep whose largest rotated |g|/sqrt(alpha beta) is <= QSP_JAC_QUAD leaves off-diagonals of
+// order n * QSP_JAC_QUAD^2 ~ 1e-16 (quadratic convergence): no verification sweep is needed.
+#define QSP_JAC_QUAD 1e-9
+
 // One full tournament sweep over `nrows` rows of W (shared memory, row stride ldw).
-// Returns the block-wide number of rotations applied.  All threads must call.
+// Returns the block-wide number of rotations above QSP_JAC_QUAD (0 = converged).  All threads must call.
 __device__ inline int jacobi_sweep_smem(cplx* W, int nrows, int ndot, int len, int ldw, int tpp, double tol2,
                                         double* red) {
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -86,7 +90,7 @@ __device__ inline int jacobi_sweep_smem(cplx* W, int nrows, int ndot, int len, i
           xw[c] = xn;
           yw[c] = yn;
         }
-        if (tl == 0) ++nrot;
+        if (tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) ++nrot;  // rotations below it leave ~1e-18: no verification sweep
       }
     }
     __syncthreads();
@@ -113,7 +117,17 @@ __device__ inline bool jacobi_rows(cplx* Wg, int nrows, int ndot, int len, cplx*
     if (sweeps_out) *sweeps_out = 0;
     return true;
   }
+  // team width per stage: as wide as the number of concurrent pairs allows (the caller's hint is
+  // sized for the whole matrix, a block pair has far fewer pairs than the CTA has lanes)
+  auto team_width = [&](int rows) {
+    const int pairs = (rows + 1) >> 1;
+    int t = 32;
+    while (t > 1 && ((int)blockDim.x / t < pairs || t > ndot)) t >>= 1;
+    return t;
+  };
+  (void)tpp;
   if (nrows <= cap_rows) {
+    tpp = team_width(nrows);
     copy_rows(Wsm, len, Wg, len, nrows, len);
     __syncthreads();
     while (sweeps < max_sweeps) {
@@ -131,6 +145,7 @@ __device__ inline bool jacobi_rows(cplx* Wg, int nrows, int ndot, int len, cplx*
     int rb = cap_rows / 2;
     const int nblk = (nrows + rb - 1) / rb;
     rb = (nrows + nblk - 1) / nblk;  // balance the blocks
+    tpp = team_width(2 * rb);
     while (sweeps < max_sweeps) {
       int nrot = 0;
       for (int bi = 0; bi < nblk; ++bi) {
@@ -182,13 +197,9 @@ __device__ int g_jvar = 0;
 #define QSP_JV() (0)
 #endif
 #ifndef QSP_JCH
-#define QSP_JCH 2
+#define QSP_JCH 2  // columns of the shared row fetched per batch in the streaming (non-HOLD) path
 #endif
-//   // columns of the shared row fetched per batch in the streaming (non-HOLD) path
-#define QSP_JPAD 32
-// A sweep whose largest rotated |g|/sqrt(alpha beta) is <= QSP_JAC_QUAD leaves off-diagonals of
-// order n * QSP_JAC_QUAD^2 ~ 1e-16 (quadratic convergence): no verification sweep is needed.
-#define QSP_JAC_QUAD 1e-9  // rows are zero-padded to a multiple of this many columns
+#define QSP_JPAD 32  // rows are zero-padded to a multiple of this many columns
 
 // Team geometry for an (nrows x ldw) problem (ldw a multiple of QSP_JPAD): tpp lanes per team,
 // np pairs per team, cpl = ldw / tpp columns per lane (<= 16; up to 8 both rows of a visit are
