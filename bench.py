@@ -364,22 +364,24 @@ def main():
         dist.destroy_process_group()
 
 
-def fp64_peak(torch, lib, dev, sms):
-    """DFMA throughput measured in-run (TFLOP/s): MEASURED_PEAKS.json has no FP64 entry."""
+def fp64_peak(torch, lib, dev, sms, tensor=False):
+    """FP64 throughput measured in-run (TFLOP/s): MEASURED_PEAKS.json has no FP64 entry.
+    tensor=False: DFMA (the pipe the kernels use); tensor=True: warp-level DMMA (mma.sync m8n8k4.f64)."""
     import ctypes
 
     out = torch.zeros(8, dtype=torch.float64, device=dev)
     s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     blocks, threads, iters = sms * 8, 256, 20000
+    probe = lib.qsp_dmma_probe if tensor else lib.qsp_dfma_probe
+    flops = blocks * (threads // 32) * iters * 8 * 512.0 if tensor else blocks * threads * iters * 32.0
     best = 0.0
     for _ in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        lib.qsp_dfma_probe(ctypes.c_void_p(out.data_ptr()), blocks, threads, iters, s)
+        probe(ctypes.c_void_p(out.data_ptr()), blocks, threads, iters, s)
         e1.record()
         torch.cuda.synchronize()
-        tf = blocks * threads * iters * 32.0 / (e0.elapsed_time(e1) * 1e-3) / 1e12
-        best = max(best, tf)
+        best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
     return best
 
 
@@ -443,6 +445,7 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
     return {"bound": "fp64", "kernel": "k_right_compress(fused inverse layer + 2chi->chi)", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+            "fp64_tensor_peak_dmma_probe": fp64_peak(torch, lib, dev, sms, tensor=True),
             "note": "achieved counts the REFERENCE's flops this launch replaces (S2+S3+S4 of SURVEY 8d: inverse layer with "
                     "SVD splits, two 2chi QR sweeps, two SVD sweeps); the device reaches the same state with one Jacobi sweep "
                     "(DESIGN.md I1-I3), so frac is an algorithmic speed figure, not pipe utilisation",

@@ -168,6 +168,9 @@ int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int nt, 
  * double-precision FMAs (flops = blocks*threads*iters*32).  bench.py times it to obtain the
  * FP64 roofline denominator, which MEASURED_PEAKS.json does not carry. */
 int qsp_dfma_probe(double* out, int blocks, int threads, int iters, void* stream);
+/* Same for the FP64 tensor pipe: `iters` rounds of 8 independent warp-level DMMA (mma.sync m8n8k4.f64),
+ * flops = blocks*(threads/32)*iters*8*512. */
+int qsp_dmma_probe(double* out, int blocks, int threads, int iters, void* stream);
 
 #ifdef __cplusplus
 }

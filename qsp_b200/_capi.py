@@ -44,6 +44,7 @@ _SIGNATURES = {
     "qsp_jacobi_variant": (None, [_i]),
     "qsp_jacobi_bench": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "qsp_dfma_probe": (_i, [_p, _i, _i, _i, _p]),
+    "qsp_dmma_probe": (_i, [_p, _i, _i, _i, _p]),
     "qsp_seq_prepare": (_i, [_p, _p, _i, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 

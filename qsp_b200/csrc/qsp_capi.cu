@@ -377,6 +377,42 @@ extern "C" int qsp_dfma_probe(double* out, int blocks, int threads, int iters, v
   return check_launch();
 }
 
+// FP64 tensor-pipe probe: warp-level DMMA (mma.sync m8n8k4, the only FP64 tensor instruction on
+// sm_100a -- tcgen05 has no f64 kind).  8 independent accumulator pairs per thread, 512 flops per
+// warp instruction.  bench.py reports it next to the DFMA figure ("why no tensor cores").
+__global__ void k_dmma_probe(double* out, int iters) {
+#ifndef QSP_EMU
+  double c[8][2];
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9 * (blockIdx.x + 1);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = k * 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[k][0]), "+d"(c[k][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+  if (s == 12345.678) out[0] = s;
+#else
+  (void)out;
+  (void)iters;
+#endif
+}
+extern "C" int qsp_dmma_probe(double* out, int blocks, int threads, int iters, void* stream) {
+  if (!out || blocks <= 0 || threads <= 0 || threads % 32) return QSP_ERR_ARG;
+#ifdef QSP_EMU
+  return QSP_ERR_UNSUPPORTED;
+#else
+  QSP_LAUNCH(k_dmma_probe, blocks, threads, 0, (qsp_stream_t)stream, out, iters);
+  ++g_launches;
+  return check_launch();
+#endif
+}
+
 // Jacobi micro-benchmark (development aid): every CTA orthogonalises its own copy of an
 // nrows x ldw matrix (W[B][nrows][ldw]) in place; sweeps[B] receives the sweep counts.
 template <int NTMAX>
