@@ -100,10 +100,12 @@ struct LCanonPlan {
   bool big;  // site matrix in the L2-resident scratch (k_left_canon_big)
 };
 static int g_force_big = 0;  // test hook (qsp_debug_flags bit 0): take the large-bond path at any size
+static int g_nt_rc = 0, g_nt_lc = 0;  // tuning hooks: threads per CTA of k_right_compress / k_left_canon (0 = planned)
 static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
   p->big = false;
   if (2 * D <= 32 * QSP_QR_MAXR && !g_force_big) {  // a column must fit one warp's registers
     p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : (D <= 48 ? 256 : 512));
+    if (g_nt_lc) p->nt = g_nt_lc;
     p->smem = lcanon_smem_bytes(D, p->nt);
     if (p->smem > d.max_smem && p->nt == 512) {
       p->nt = 256;
@@ -129,7 +131,10 @@ struct RCompressPlan {
 };
 static bool plan_rcompress(int Din, int Dout, const DevInfo& d, RCompressPlan* p) {
   const int dm = imax(Din / 2, Dout);
-  p->nt = dm >= 48 ? 512 : (dm >= 16 ? 256 : (dm >= 4 ? 128 : 64));
+  // eight lanes per Jacobi pair (2 dm rows -> dm pairs): the power-of-two bonds then hit the compile-time
+  // specialisations of the register-resident Jacobi (chi = 16 / 32 / 64 -> 128 / 256 / 512 threads)
+  p->nt = dm >= 48 ? 512 : (dm >= 24 ? 256 : (dm >= 4 ? 128 : 64));  // measured: chi 8..16 -> 128, 24..32 -> 256, 48.. -> 512
+  if (g_nt_rc) p->nt = g_nt_rc;
   int tpp = 32;
   while (tpp > 2 && p->nt / tpp < imin(Dout, Din)) tpp >>= 1;  // >= one team per pair when possible
   p->tpp = tpp;
@@ -206,7 +211,11 @@ extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, in
                                  size_t work_bytes, void* stream) {
   return left_canonize_live(mps, bonds, B, L, D, D, status, work, work_bytes, stream);
 }
-extern "C" void qsp_debug_flags(int flags) { g_force_big = flags & 1; }
+extern "C" void qsp_debug_flags(int flags) {
+  g_force_big = flags & 1;
+  g_nt_rc = (flags >> 8) & 0xfff;   // bits 8..19: threads per CTA of k_right_compress
+  g_nt_lc = (flags >> 20) & 0xfff;  // bits 20..31: threads per CTA of k_left_canon
+}
 
 static int rcompress_grid(int B, const RCompressPlan& p, const DevInfo& d) {
   return grid_for(B, blocks_per_sm((const void*)k_right_compress, p.nt, p.smem), d);

@@ -21,6 +21,20 @@ typedef cudaStream_t qsp_stream_t;
 
 #include <stdint.h>
 
+// A pointer handed to an out-of-line device function is generic to the compiler even when every
+// caller passes shared memory.  QSP_ASSUME_SHARED(flag, p) re-derives p from the dynamic shared
+// window (base + 32-bit offset) when the compile-time flag is set, so its accesses become LDS/STS.
+#ifdef QSP_EMU
+#define QSP_ASSUME_SHARED(flag, p) ((void)0)
+#else
+#define QSP_ASSUME_SHARED(flag, p)                                                                        \
+  do {                                                                                                    \
+    if (flag)                                                                                             \
+      p = (decltype(p))(qsp_dyn_smem +                                                                    \
+                        ((unsigned)__cvta_generic_to_shared(p) - (unsigned)__cvta_generic_to_shared(qsp_dyn_smem))); \
+  } while (0)
+#endif
+
 #ifdef QSP_EMU
 inline long long qsp_clock() { return 0; }
 inline double qsp_rsqrt(double x) { return 1.0 / sqrt(x); }

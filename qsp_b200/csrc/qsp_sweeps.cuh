@@ -101,7 +101,9 @@ __device__ __forceinline__ void qr_apply_reflector(const cplx (&vr)[MAXR], cplx*
   }
 }
 
-template <int MAXR>
+// SHARED: S, R, tau, beta live in the dynamic shared window; they are rebuilt from their offsets inside the
+// (out-of-line) function so that the accesses compile to LDS/STS instead of generic loads.
+template <int MAXR, bool SHARED>
 __device__ __noinline__ void cta_householder_qr_t(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
                                                   long long* pc);
 
@@ -109,20 +111,24 @@ template <bool BIG>
 __device__ __forceinline__ void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
                                                    long long* pc) {
   if (BIG && m > 32 * QSP_QR_MAXR)
-    cta_householder_qr_t<QSP_QR_MAXR_BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
+    cta_householder_qr_t<QSP_QR_MAXR_BIG, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
   else if (m <= 32)
-    cta_householder_qr_t<1>(S, m, n, ldS, R, ldR, tau, beta, pc);
+    cta_householder_qr_t<1, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
   else if (m <= 64)
-    cta_householder_qr_t<2>(S, m, n, ldS, R, ldR, tau, beta, pc);
+    cta_householder_qr_t<2, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
   else if (m <= 128)
-    cta_householder_qr_t<4>(S, m, n, ldS, R, ldR, tau, beta, pc);
+    cta_householder_qr_t<4, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
   else
-    cta_householder_qr_t<QSP_QR_MAXR>(S, m, n, ldS, R, ldR, tau, beta, pc);
+    cta_householder_qr_t<QSP_QR_MAXR, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
 }
 
-template <int MAXR>
+template <int MAXR, bool SHARED>
 __device__ __noinline__ void cta_householder_qr_t(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
                                                   long long* pc) {
+  QSP_ASSUME_SHARED(SHARED, S);
+  QSP_ASSUME_SHARED(SHARED, R);
+  QSP_ASSUME_SHARED(SHARED, tau);
+  QSP_ASSUME_SHARED(SHARED, beta);
   long long tck = qsp_clock();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const int K = imin(m, n);

@@ -1,4 +1,2 @@
-mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; echo "bench rc=$?"
-python -c "
-import json; j=json.load(open('gpurun_out/bench_r1.json')); r=j['roofline']; print(j['value'], j['e2e']['value'], r['peak'], r.get('fp64_tensor_peak_dmma_probe'), r['frac'], j['cpu_baseline']['value'])"
+run() { f=$(( ($2<<8) )); echo "chi=$1 rc_nt=$2"; QSP_DEBUG_FLAGS=$f timeout 200 python scripts/probe.py 50 $1 4 1024 2 2>&1 | tail -1; }
+run 8 0; run 8 128; run 12 0; run 12 64; run 12 256; run 16 0; run 24 0; run 24 128; run 48 0; run 48 256

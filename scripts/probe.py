@@ -10,6 +10,8 @@ reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 enc = os.environ.get("PROBE_ENC", "1") == "1"
 dev = torch.device("cuda:0")
 eng = Engine()
+if os.environ.get('QSP_DEBUG_FLAGS'):
+    eng.lib.qsp_debug_flags(int(os.environ['QSP_DEBUG_FLAGS'], 0))
 raw, b0 = synth_batch(torch, B, L, chi, dev, 1)
 t0 = time.time(); st = eng.prepare_target(raw, b0); torch.cuda.synchronize()
 print(f"prepare_target {time.time()-t0:.3f}s status {int(st.max())} maxbond {int(b0.max())}", flush=True)
