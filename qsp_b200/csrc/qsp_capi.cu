@@ -104,7 +104,7 @@ static int g_nt_rc = 0, g_nt_lc = 0;  // tuning hooks: threads per CTA of k_righ
 static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
   p->big = false;
   if (2 * D <= 32 * QSP_QR_MAXR && !g_force_big) {  // a column must fit one warp's registers
-    p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : (D <= 48 ? 256 : 512));
+    p->nt = D <= 8 ? 64 : (D <= 24 ? 128 : (D <= 48 ? 256 : 512));  // measured at chi = 8, 16, 32, 64
     if (g_nt_lc) p->nt = g_nt_lc;
     p->smem = lcanon_smem_bytes(D, p->nt);
     if (p->smem > d.max_smem && p->nt == 512) {
