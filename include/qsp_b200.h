@@ -123,7 +123,7 @@ int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, int D, doubl
  * target (core.py:217-221, sequential.py:67-70, tsp.py:130-132): result[b] = <target_b| U_0 ... U_{n-1} |0..0>
  * for G[n][B][L][4][4], kind[n][B][L].  Every forward layer is applied exactly (bonds double); the
  * reference's cutoff-only compress('right') after each layer does not change the state and is only run
- * when the doubled bonds would not fit (more than 8 layers on chains of at most 11 sites). */
+ * when the doubled bonds would not fit (more than 8 layers on chains of at most 15 sites). */
 size_t qsp_encoded_overlap_workspace_bytes(int B, int L, int D, int layers);
 int qsp_encoded_overlap(const qsp_c128* G, const int32_t* kind, int n, const qsp_c128* target,
                         const int32_t* target_bonds, int B, int L, int D, double cutoff, qsp_c128* result,
