@@ -86,29 +86,31 @@ class CxU3Circuit:
         self = cls(gl.num_qubits)
         self.source = gl
         pending = [None] * gl.num_qubits
-        rng = np.random.default_rng(7)
 
         def push(q, m):
             pending[q] = m if pending[q] is None else m @ pending[q]
 
+        mats = []  # flushed one-qubit products; their u3 parameters are computed in one batch at the end
+
         def flush(q):
             m, pending[q] = pending[q], None
-            if m is None:
-                return
-            th, ph, la, ga = kak.u3_params(m)
-            self.global_phase += ga
-            if np.abs(kak.u3_matrix(th, ph, la) - np.eye(2)).max() > atol:
-                self.gates.append(("u3", [q], (th, ph, la)))
+            if m is not None:
+                self.gates.append(("u3", [q], len(mats)))
+                mats.append(m)
 
-        for u, qs in gl.gates:
+        # all two-qubit unitaries of the circuit are synthesised in one batched call
+        two = [k for k, (_, qs) in enumerate(gl.gates) if len(qs) == 2]
+        dec = kak.decompose_two_qubit_batch(np.stack([gl.gates[k][0] for k in two])) if two else None
+        where = {k: i for i, k in enumerate(two)}
+        for k, (u, qs) in enumerate(gl.gates):
             if len(qs) == 1:
                 push(qs[0], u)
                 continue
             # matrix index = 2 * bit(qs[1]) + bit(qs[0]): left factor <-> qs[1], right factor <-> qs[0]
             side = (qs[1], qs[0])
-            phase, ops = kak.decompose_two_qubit(u, rng)
-            self.global_phase += float(np.angle(phase))
-            for op in ops:
+            i = where[k]
+            self.global_phase += float(np.angle(dec["phase"][i]))
+            for op in kak.ops_from_batch(dec, i):
                 if op[0] == "u":
                     push(side[op[1]], op[2])
                 else:
@@ -118,6 +120,13 @@ class CxU3Circuit:
                     self.gates.append(("cx", [c, t], ()))
         for q in range(gl.num_qubits):
             flush(q)
+        if mats:
+            th, ph, la, ga = kak.u3_params_batch(np.stack(mats))
+            self.global_phase += float(ga.sum())
+            # a product that is a phase times the identity is dropped: theta = 0 and phi + lam = 0 (mod 2 pi)
+            ident = (np.abs(np.sin(th / 2)) < atol) & (np.abs(np.exp(1j * (ph + la)) - 1.0) < atol)
+            self.gates = [g if g[0] == "cx" else ("u3", g[1], (float(th[g[2]]), float(ph[g[2]]), float(la[g[2]])))
+                          for g in self.gates if g[0] == "cx" or not ident[g[2]]]
         return self
 
     def size(self):
@@ -195,7 +204,9 @@ def circuit_from_unitary_layers(unitary_layers, L, target_mps=None, device="cuda
     if L <= 16 and arrays is not None:
         import torch
 
-        vec = shadow.statevector(device)
-        orig = _dense_from_mps(arrays, device)
+        # 2^L amplitudes: below ~4k the simulation is launch-bound on a GPU, so tiny registers run on the host
+        sim_dev = "cpu" if L <= 12 else device
+        vec = shadow.statevector(sim_dev)
+        orig = _dense_from_mps(arrays, sim_dev)
         overlap_from_seq_circ = float(torch.abs(torch.sum(torch.conj(orig) * vec)).item())
     return circ, overlap_from_seq_circ

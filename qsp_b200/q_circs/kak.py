@@ -54,109 +54,186 @@ def u3_params(a):
     return float(theta), float(phi), float(lam), float(gamma)
 
 
+def u3_params_batch(a):
+    """u3_params for a[n, 2, 2]: arrays (theta, phi, lam, gamma)"""
+    eps = 1e-12
+    a00, a01, a10, a11 = a[:, 0, 0], a[:, 0, 1], a[:, 1, 0], a[:, 1, 1]
+    theta = 2.0 * np.arctan2(np.abs(a10), np.abs(a00))
+    gamma = np.where(np.abs(a00) > eps, np.angle(a00), 0.0)
+    phi = np.where(np.abs(a10) > eps, np.angle(a10) - gamma, 0.0)
+    lam = np.where(np.abs(a01) > eps, np.angle(-a01) - gamma, np.angle(a11) - gamma - phi)
+    return theta, phi, lam, gamma
+
+
 def _su4(u):
-    """(u / det^{1/4}, phase) with u = phase * su"""
+    """(u / det^{1/4}, phase) with u = phase * su; u: (..., 4, 4)"""
     ph = np.linalg.det(u) ** 0.25
-    return u / ph, ph
+    return u / ph[..., None, None], ph
 
 
 def _diag_symmetric_unitary(m2, rng):
-    """Real orthogonal P with P^T m2 P diagonal, for a complex symmetric unitary m2 (its real and
-    imaginary parts commute, so a generic real combination shares their eigenvectors)."""
+    """Real orthogonal P[n] with P^T m2 P diagonal, for complex symmetric unitaries m2[n] (their real and
+    imaginary parts commute, so a generic real combination shares their eigenvectors).  Batched; items whose
+    random combination happens to be degenerate are redone with fresh coefficients."""
+    n = m2.shape[0]
+    lam = np.empty((n, 4), dtype=np.complex128)
+    p = np.empty((n, 4, 4), dtype=np.float64)
+    todo = np.arange(n)
     for _ in range(64):
         r, t = rng.normal(size=2)
-        _, p = np.linalg.eigh(r * m2.real + t * m2.imag)
-        d = p.T @ m2 @ p
-        if np.abs(d - np.diag(np.diag(d))).max() < 1e-11:
-            return np.diag(d).copy(), p
+        _, q = np.linalg.eigh(r * m2[todo].real + t * m2[todo].imag)
+        d = np.swapaxes(q, 1, 2) @ m2[todo] @ q
+        dd = np.diagonal(d, axis1=1, axis2=2)
+        off = np.abs(d - dd[:, :, None] * np.eye(4)).max(axis=(1, 2))
+        ok = off < 1e-11
+        lam[todo[ok]], p[todo[ok]] = dd[ok], q[ok]
+        todo = todo[~ok]
+        if todo.size == 0:
+            return lam, p
     raise np.linalg.LinAlgError("simultaneous diagonalisation failed")
 
 
 def _kron_factor(m):
-    """m = e^{i g} a (x) b with a, b in SU(2) -> (a, b, e^{i g})"""
-    r = m.reshape(2, 2, 2, 2).transpose(0, 2, 1, 3).reshape(4, 4)
+    """m[n] = e^{i g} a (x) b with a, b in SU(2) -> (a[n], b[n], e^{i g}[n], residual[n]); the residual is the
+    second singular value of the (a, b) rearrangement relative to the first (0 for an exact product)."""
+    n = m.shape[0]
+    r = m.reshape(n, 2, 2, 2, 2).transpose(0, 1, 3, 2, 4).reshape(n, 4, 4)
     u, s, vh = np.linalg.svd(r)
-    if s[1] > 1e-7 * s[0]:
-        raise np.linalg.LinAlgError("not a product of one-qubit unitaries")
-    a = (u[:, 0] * np.sqrt(s[0])).reshape(2, 2)
-    b = (vh[0] * np.sqrt(s[0])).reshape(2, 2)
+    a = (u[:, :, 0] * np.sqrt(s[:, :1])).reshape(n, 2, 2)
+    b = (vh[:, 0, :] * np.sqrt(s[:, :1])).reshape(n, 2, 2)
     da, db = np.sqrt(np.linalg.det(a) + 0j), np.sqrt(np.linalg.det(b) + 0j)
-    return a / da, b / db, da * db
+    da = np.where(np.abs(da) < 1e-150, 1.0, da)  # singular factors only occur for non-products (result unused)
+    db = np.where(np.abs(db) < 1e-150, 1.0, db)
+    return a / da[:, None, None], b / db[:, None, None], da * db, s[:, 1] / np.maximum(s[:, 0], 1e-300)
+
+
+def _kron(a, b):
+    """batched Kronecker product of (n, 2, 2) factors"""
+    return np.einsum("nij,nkl->nikjl", a, b).reshape(a.shape[0], 4, 4)
+
+
+def _rz(t):
+    z = np.zeros((t.shape[0], 2, 2), dtype=np.complex128)
+    z[:, 0, 0], z[:, 1, 1] = np.exp(-0.5j * t), np.exp(0.5j * t)
+    return z
+
+
+def _ry(t):
+    c, s = np.cos(t / 2), np.sin(t / 2)
+    z = np.empty((t.shape[0], 2, 2), dtype=np.complex128)
+    z[:, 0, 0], z[:, 0, 1], z[:, 1, 0], z[:, 1, 1] = c, -s, s, c
+    return z
+
+
+def _weyl_from_spectrum(up, lam, p):
+    """Weyl coordinates from the eigen-decomposition up^T up = p diag(lam) p^T (batched)."""
+    p = p.copy()
+    neg = np.linalg.det(p) < 0
+    p[neg, :, 0] *= -1
+    d = 0.5 * np.angle(lam)
+    k1 = up @ p * np.exp(-1j * d)[:, None, :]  # real orthogonal; SO(4) needs det +1
+    d[np.linalg.det(k1).real < 0, 0] += np.pi
+    abc = np.linalg.solve(_WEYL_BASIS, d.T).T
+    return abc[:, 0], abc[:, 1], abc[:, 2]
 
 
 def weyl_coordinates(u, rng=None):
     """(a, b, c) with u locally equivalent to exp(i(a XX + b YY + c ZZ)) (one representative, not
     reduced to the Weyl chamber)."""
     rng = rng or np.random.default_rng(7)
-    su, _ = _su4(np.asarray(u, dtype=np.complex128))
+    su, _ = _su4(np.asarray(u, dtype=np.complex128)[None])
     up = _MAGIC.conj().T @ su @ _MAGIC
-    lam, p = _diag_symmetric_unitary(up.T @ up, rng)
-    if np.linalg.det(p) < 0:
-        p[:, 0] *= -1
-    d = 0.5 * np.angle(lam)
-    k1 = up @ p @ np.diag(np.exp(-1j * d))   # real orthogonal; SO(4) needs det +1
-    if np.linalg.det(k1).real < 0:
-        d[0] += np.pi
-    a, b, c, _ = np.linalg.solve(_WEYL_BASIS, d)
-    return float(a), float(b), float(c)
+    lam, p = _diag_symmetric_unitary(np.swapaxes(up, 1, 2) @ up, rng)
+    a, b, c = _weyl_from_spectrum(up, lam, p)
+    return float(a[0]), float(b[0]), float(c[0])
+
+
+def _core_batch(a, b, c):
+    t1, t2, t3 = -2 * a - np.pi / 2, -2 * b - np.pi / 2, 2 * c - np.pi / 2
+    eye = np.broadcast_to(_I2, (a.shape[0], 2, 2))
+    w = _CX @ _kron(_ry(t3), eye) @ _XC @ _kron(_ry(t2), _rz(t1)) @ _CX
+    return w, t1, t2, t3
 
 
 def three_cx_core(a, b, c):
-    t1, t2, t3 = -2 * a - np.pi / 2, -2 * b - np.pi / 2, 2 * c - np.pi / 2
-    w = _CX @ np.kron(ry(t3), _I2) @ _XC @ np.kron(ry(t2), rz(t1)) @ _CX
-    return w, (t1, t2, t3)
+    w, t1, t2, t3 = _core_batch(np.atleast_1d(float(a)), np.atleast_1d(float(b)), np.atleast_1d(float(c)))
+    return w[0], (float(t1[0]), float(t2[0]), float(t3[0]))
 
 
-def _locals_between(u, w, rng):
-    """(phase, L1, L2), L1 and L2 in SU(2) (x) SU(2), with u = phase * L1 w L2."""
-    us, phu = _su4(u)
+def decompose_two_qubit_batch(u, rng=None):
+    """u[n] (4x4 unitaries on kron(left, right)) -> dict of arrays:
+    product[n] (bool: no CNOT needed), phase[n], a2, b2 (first one-qubit gates, left / right), t1, t2, t3
+    (core angles), a1, b1 (last one-qubit gates).  For product gates only a2, b2 and phase are meaningful."""
+    rng = rng or np.random.default_rng(7)
+    u = np.ascontiguousarray(u, dtype=np.complex128)
+    n = u.shape[0]
+    out = {k: np.zeros((n, 2, 2), dtype=np.complex128) for k in ("a1", "b1", "a2", "b2")}
+    out.update({k: np.zeros(n) for k in ("t1", "t2", "t3")})
+    out["phase"] = np.ones(n, dtype=np.complex128)
+    a0, b0, ph0, res = _kron_factor(u)
+    prod = (res < 1e-7) & (np.abs(ph0[:, None, None] * _kron(a0, b0) - u).max(axis=(1, 2)) < 1e-10)
+    out["product"] = prod
+    out["a2"][prod], out["b2"][prod], out["phase"][prod] = a0[prod], b0[prod], ph0[prod]
+    idx = np.nonzero(~prod)[0]
+    if idx.size == 0:
+        return out
+    v = u[idx]
+    us, phu = _su4(v)
+    up = _MAGIC.conj().T @ us @ _MAGIC
+    lu, p = _diag_symmetric_unitary(np.swapaxes(up, 1, 2) @ up, rng)
+    a, b, c = _weyl_from_spectrum(up, lu, p)
+    w, t1, t2, t3 = _core_batch(a, b, c)
     ws, phw = _su4(w)
-    up, wp = _MAGIC.conj().T @ us @ _MAGIC, _MAGIC.conj().T @ ws @ _MAGIC
-    lu, p = _diag_symmetric_unitary(up.T @ up, rng)
-    best = None
-    for k in (0, 1):  # det^{1/4} is defined up to i^k: the spectra agree up to (-1)^k
+    wp = _MAGIC.conj().T @ ws @ _MAGIC
+    # det^{1/4} is defined up to i^k: the spectra of up^T up and wp^T wp agree up to (-1)^k and a permutation
+    perms = np.array(_PERMS)
+    best_e = np.full(idx.size, np.inf)
+    best_k = np.zeros(idx.size, dtype=int)
+    best_q = np.zeros((idx.size, 4, 4))
+    for k in (0, 1):
         wk = wp * (1j ** k)
-        lw, q = _diag_symmetric_unitary(wk.T @ wk, rng)
-        for perm in _PERMS:
-            e = np.abs(lu - lw[perm]).max()
-            if best is None or e < best[0]:
-                best = (e, k, perm, q, wk)
-    e, k, perm, q, wk = best
-    if e > 1e-7:
+        lw, q = _diag_symmetric_unitary(np.swapaxes(wk, 1, 2) @ wk, rng)
+        e = np.abs(lu[:, None, :] - lw[:, perms]).max(axis=2)  # (n, 24)
+        j = e.argmin(axis=1)
+        ej = e[np.arange(idx.size), j]
+        better = ej < best_e
+        qp = np.take_along_axis(q, perms[j][:, None, :].repeat(4, axis=1), axis=2)  # columns permuted
+        best_e[better], best_k[better], best_q[better] = ej[better], k, qp[better]
+    if best_e.max() > 1e-7:
         raise np.linalg.LinAlgError("template is not locally equivalent to the unitary")
-    q = q[:, perm]
-    if np.linalg.det(q) * np.linalg.det(p) < 0:
-        p = p.copy()
-        p[:, 0] *= -1
-    o2 = q @ p.T
-    o1 = up @ o2.T @ wk.conj().T
-    l1, l2 = _MAGIC @ o1.real @ _MAGIC.conj().T, _MAGIC @ o2 @ _MAGIC.conj().T
-    return phu / phw * (1j ** k), l1, l2
+    wk = wp * (1j ** best_k)[:, None, None]
+    p = p.copy()
+    flip = np.linalg.det(best_q) * np.linalg.det(p) < 0
+    p[flip, :, 0] *= -1
+    o2 = best_q @ np.swapaxes(p, 1, 2)
+    o1 = up @ np.swapaxes(o2, 1, 2) @ np.conj(np.swapaxes(wk, 1, 2))
+    l1 = _MAGIC @ o1.real @ _MAGIC.conj().T
+    l2 = _MAGIC @ o2 @ _MAGIC.conj().T
+    a1, b1, p1, _ = _kron_factor(l1)
+    a2, b2, p2, _ = _kron_factor(l2)
+    out["a1"][idx], out["b1"][idx], out["a2"][idx], out["b2"][idx] = a1, b1, a2, b2
+    out["t1"][idx], out["t2"][idx], out["t3"][idx] = t1, t2, t3
+    out["phase"][idx] = phu / phw * (1j ** best_k) * p1 * p2
+    return out
+
+
+def ops_from_batch(dec, i):
+    """time-ordered op list of gate i of a decompose_two_qubit_batch result: ("u", side, 2x2 matrix) with
+    side 0 = left / 1 = right factor, and ("cx", control_side, target_side)."""
+    if dec["product"][i]:
+        return [("u", 0, dec["a2"][i]), ("u", 1, dec["b2"][i])]
+    return [("u", 0, dec["a2"][i]), ("u", 1, dec["b2"][i]), ("cx", 0, 1), ("u", 0, ry(dec["t2"][i])), ("u", 1, rz(dec["t1"][i])),
+            ("cx", 1, 0), ("u", 0, ry(dec["t3"][i])), ("cx", 0, 1), ("u", 0, dec["a1"][i]), ("u", 1, dec["b1"][i])]
 
 
 def decompose_two_qubit(u, rng=None):
-    """u (4x4 unitary on kron(left, right)) -> (global phase, ops in time order); ops are
-    ("u", side, 2x2 matrix) with side 0 = left / 1 = right factor, and ("cx", control_side, target_side)."""
-    rng = rng or np.random.default_rng(7)
-    u = np.asarray(u, dtype=np.complex128)
-    try:  # a product of one-qubit gates needs no CNOT
-        a0, b0, ph = _kron_factor(u)
-        if np.abs(ph * np.kron(a0, b0) - u).max() < 1e-10:
-            return ph, [("u", 0, a0), ("u", 1, b0)]
-    except np.linalg.LinAlgError:
-        pass
-    a, b, c = weyl_coordinates(u, rng)
-    w, (t1, t2, t3) = three_cx_core(a, b, c)
-    ph, l1, l2 = _locals_between(u, w, rng)
-    a1, b1, p1 = _kron_factor(l1)
-    a2, b2, p2 = _kron_factor(l2)
-    ops = [("u", 0, a2), ("u", 1, b2), ("cx", 0, 1), ("u", 0, ry(t2)), ("u", 1, rz(t1)), ("cx", 1, 0), ("u", 0, ry(t3)),
-           ("cx", 0, 1), ("u", 0, a1), ("u", 1, b1)]
-    return ph * p1 * p2, ops
+    """one gate: (global phase, ops in time order), see ops_from_batch"""
+    dec = decompose_two_qubit_batch(np.asarray(u, dtype=np.complex128)[None], rng)
+    return complex(dec["phase"][0]), ops_from_batch(dec, 0)
 
 
 def ops_to_matrix(ops):
-    """4x4 matrix of a decompose_two_qubit op list (tests)."""
+    """4x4 matrix of an op list (tests)."""
     m = np.eye(4, dtype=np.complex128)
     for op in ops:
         if op[0] == "u":
