@@ -235,6 +235,55 @@ def test_pipeline_chi64(drv):
     _check_pipeline(drv, tg, 2, 64, 64)
 
 
+def test_pipeline_full_headline_size(drv):
+    """BASELINE configs[3] at its full per-instance size (L=100, chi=64, compression to 64), one instance, two
+    layers against the oracle (about 15 s of CPU): overlaps, D=2 singular values of both layers, and -- the strong
+    check at this size, where the overlaps themselves are ~1e-8 -- the fidelity of the final disentangled state."""
+    tgt = _prepared(O.random_mps(100, 64, 5))
+    r = _check_pipeline(drv, [tgt], 2, 64, 64, same_convention=False)
+    sc = O.sequential_unitary_circuit(tgt, 2, completion="canonical", do_compression=True, max_bond_dim=64)
+    assert np.abs(np.array(sc["disentangled_mps_overlaps"]) - r["dis"][:, 0]).max() < 1e-10
+    assert np.abs(np.array(sc["overlaps"]) - r["overlaps"][[0, 1], 0]).max() < 1e-10
+    fin = unpack_batch(r["final"], r["final_bonds"])[0]
+    assert O.bonds_of(fin) == O.bonds_of(sc["final_mps"])
+    assert abs(O.inner(fin, sc["final_mps"]) - 1.0) < 1e-9
+    assert abs(O.inner(fin, fin) - 1.0) < 1e-12
+
+
+def test_full_size_batch_properties(drv):
+    """Size-independent properties at the headline shape with more instances than SMs (L=100, chi=64, B=150,
+    two layers): copies of one input placed at different batch positions give bit-identical results whatever CTA
+    picks them up; every gate is unitary; the disentangled state stays normalised; layer by layer |<0..0|psi>| grows."""
+    import torch
+
+    from bench import synth_batch
+    from qsp_b200.engine import Engine
+
+    eng = Engine()
+    B, L, chi, layers = 150, 100, 64, 2
+    raw, bonds = synth_batch(torch, B, L, chi, eng.device, 11)
+    for k in (77, 149):
+        raw[k], bonds[k] = raw[0], bonds[0]
+    assert int(eng.prepare_target(raw, bonds).max()) == 0
+    res = eng.seq_prepare(raw, bonds, layers, max_bond=chi, want_final=True)
+    assert int(res.status.max()) == 0
+    for k in (77, 149):
+        assert torch.equal(res.G[:, k], res.G[:, 0]) and torch.equal(res.dis_overlaps[:, k], res.dis_overlaps[:, 0])
+        assert torch.equal(res.overlaps[:, k], res.overlaps[:, 0]) and torch.equal(res.final_mps[k], res.final_mps[0])
+    G = res.G.reshape(-1, 4, 4)
+    kind = res.kind.reshape(-1)
+    eye = torch.eye(4, dtype=G.dtype, device=G.device)
+    g2 = G[kind == 2]
+    assert float((g2 @ g2.conj().transpose(1, 2) - eye).abs().max()) < 1e-12
+    g1 = G[kind == 1][:, :2, :2]
+    assert float((g1 @ g1.conj().transpose(1, 2) - eye[:2, :2]).abs().max()) < 1e-12
+    assert int((kind == 2).sum()) == layers * B * (L - 1) and int((kind == 1).sum()) == layers * B
+    # site 0 is the orthogonality centre of the right-canonical result: its norm is the norm of the state
+    nrm = res.final_mps[:, 0].abs().pow(2).sum(dim=(1, 2, 3))
+    assert float((nrm - 1.0).abs().max()) < 1e-12
+    assert float(res.dis_overlaps[1].abs().mean()) > float(res.dis_overlaps[0].abs().mean())
+
+
 @pytest.mark.parametrize("L,chi,layers,no_comp", [(16, 128, 2, False), (18, 256, 1, False), (14, 32, 2, True)])
 def test_pipeline_large_bonds(drv, L, chi, layers, no_comp):
     """bonds beyond what fits shared memory (BASELINE configs[4] has chi = 256): the sweeps run out of the
