@@ -249,9 +249,21 @@ __device__ __forceinline__ void jacobi_rotation(double al, double be, double gx,
 // the end of every sweep (they only shrink, by c >= 1/sqrt 2 per rotation).
 // They are used where both rows of a visit are register resident (HOLD); the 16-columns-per-lane
 // variant sits at the 128-register limit and keeps plain rotations (the extra scalars spill).
+// Optional input / output of the register path (saves two passes over the matrix in the caller):
+//   src        rows are loaded from here instead of Wg (row stride src_ld, src_cols live columns, zero beyond);
+//              the orthogonalised rows are still written to Wg
+//   norms_off  shared-memory offset of a double[nrows] that receives the SQUARED row norms over the Gram columns
+//              (< 0: none); norms_done is set when they were written
+struct JacobiIO {
+  const cplx* src;
+  int src_ld, src_cols;
+  int norms_off;
+  bool norms_done;
+};
+
 template <int CPL, int NP, bool HOLD, int TPPC = 0, bool FULL = false, int FASTSEL = -1>
 __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int jlen_, int s_off, int tpp_, double tol2,
-                                            int max_sweeps, int red_off, int* sweeps_out) {
+                                            int max_sweeps, int red_off, int* sweeps_out, JacobiIO* io = nullptr) {
   constexpr bool FAST = FASTSEL < 0 ? HOLD : (FASTSEL != 0);
   const int tpp = TPPC > 0 ? TPPC : tpp_;
   const int jlen = FULL ? CPL : jlen_;
@@ -265,17 +277,23 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
   double* dS = (double*)(S + (long)ne * ldw);  // scales of the shared (even-position) rows
   cplx R[NP][CPL];
   double dr[NP];
+  {
+    const bool ext = io && io->src;
+    const cplx* src = ext ? io->src : Wg;
+    const long sld = ext ? io->src_ld : ldw;
+    const int scols = ext ? io->src_cols : ldw;
 #pragma unroll
-  for (int q = 0; q < NP; ++q) {
-    const int p = team * NP + q;
-    dr[q] = 1.0;
+    for (int q = 0; q < NP; ++q) {
+      const int p = team * NP + q;
+      dr[q] = 1.0;
 #pragma unroll
-    for (int j = 0; j < CPL; ++j)
-      R[q][j] = (p < no && j < jlen) ? Wg[(long)(2 * p + 1) * ldw + tl + j * tpp] : cmake(0.0, 0.0);
-  }
-  for (int idx = tid; idx < ne * ldw; idx += nt) {
-    const int r = idx / ldw, c = idx - r * ldw;
-    S[idx] = Wg[(long)(2 * r) * ldw + c];
+      for (int j = 0; j < CPL; ++j)
+        R[q][j] = (p < no && j < jlen && tl + j * tpp < scols) ? src[(long)(2 * p + 1) * sld + tl + j * tpp] : cmake(0.0, 0.0);
+    }
+    for (int idx = tid; idx < ne * ldw; idx += nt) {
+      const int r = idx / ldw, c = idx - r * ldw;
+      S[idx] = (c < scols) ? src[(long)(2 * r) * sld + c] : cmake(0.0, 0.0);
+    }
   }
   for (int idx = tid; idx < ne; idx += nt) dS[idx] = 1.0;
   __syncthreads();
@@ -463,6 +481,32 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
     const int r = idx / ldw, c = idx - r * ldw;
     Wg[(long)(2 * r) * ldw + c] = S[idx];
   }
+  if (io && io->norms_off >= 0) {
+    // squared row norms over the Gram columns while the rows are still on chip
+    double* nrm = (double*)(QSP_SMEM_BASE() + io->norms_off);
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      const int p = team * NP + q;
+      double n2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+        if (j < jdot) n2 = fma(R[q][j].x, R[q][j].x, fma(R[q][j].y, R[q][j].y, n2));
+      for (int o = tpp >> 1; o > 0; o >>= 1) n2 += shfl_xor_d(n2, o);
+      if (tl == 0 && p < no) nrm[2 * p + 1] = n2;
+    }
+    for (int s0 = 0; s0 < ne; s0 += nt / tpp) {  // warp-uniform trip count (shuffles inside)
+      const int slot = s0 + team;
+      const cplx* xs = S + (long)(slot < ne ? slot : 0) * ldw + tl;
+      double n2 = 0.0;
+      for (int j = 0; j < jdot; ++j) {
+        const cplx v = xs[j * tpp];
+        n2 = fma(v.x, v.x, fma(v.y, v.y, n2));
+      }
+      for (int o = tpp >> 1; o > 0; o >>= 1) n2 += shfl_xor_d(n2, o);
+      if (tl == 0 && slot < ne) nrm[2 * slot] = n2;
+    }
+    io->norms_done = true;  // (io is per-thread: every thread records it)
+  }
   __syncthreads();
   if (sweeps_out) *sweeps_out = sweeps;
   return conv;
@@ -479,7 +523,7 @@ __host__ __device__ inline bool jacobi_oe_fits(int nt, int nrows, int ldw, int c
 // Dispatcher.  Wg: nrows x ldw (row stride ldw), first ndotp columns enter the Gram entries;
 // for the register path ldw and ndotp are multiples of QSP_JPAD (zero padded).
 __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, cplx* Wsm, int cap_elems, int tpp_hint,
-                                       double tol2, int max_sweeps, double* red, int* sweeps_out) {
+                                       double tol2, int max_sweeps, double* red, int* sweeps_out, JacobiIO* io = nullptr) {
   if (nrows <= 1) {
     if (sweeps_out) *sweeps_out = 0;
     return true;
@@ -490,13 +534,13 @@ __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, 
     const int jlen = ldw / tpp, jdot = (ndotp + tpp - 1) / tpp;
     const int s_off = (int)((char*)Wsm - QSP_SMEM_BASE()), r_off = (int)((char*)red - QSP_SMEM_BASE());
 #define QSP_OE(C, N, H) \
-  jacobi_rows_oe<C, N, H>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out)
+  jacobi_rows_oe<C, N, H>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, r_off, sweeps_out, io)
 #ifndef QSP_MAIN_FAST
 #define QSP_MAIN_FAST 0  // scaled rotations in the 16-columns-per-lane variant (register limited: off)
 #endif
 #define QSP_OEF(C, H, T) \
   jacobi_rows_oe<C, 1, H, T, true, ((C) == 16 ? QSP_MAIN_FAST : -1)>(Wg, nrows, jdot, jlen, s_off, tpp, tol2, max_sweeps, \
-                                                                       r_off, sweeps_out)
+                                                                       r_off, sweeps_out, io)
     if (np == 1 && jdot == jlen) {  // power-of-two problems of the layer loop and of the input pipeline
       if (tpp == 8) {
         if (jlen == 16) return QSP_OEF(16, false, 8);  // 128 x 128 (chi = 64 bulk)

@@ -554,9 +554,19 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       const int ndotp = ((ndot + tq - 1) / tq) * tq;
       int len = modeC ? ndotp + c : ndotp;
       len = ((len + tq - 1) / tq) * tq;
-      if (!jacobi_oe_fits(nt, nrows, len, P.cap_rows_elems) && !modeC) len = c;  // generic path: no padding needed
+      const bool oe = nrows >= 2 && jacobi_oe_fits(nt, nrows, len, P.cap_rows_elems);  // register-resident Jacobi takes it
+      if (!oe && !modeC) len = c;  // generic path: no padding needed
       const int joff = modeC ? ndotp : 0;  // first column of the appended identity
-      if (modeC) {
+      JacobiIO io;
+      io.src = nullptr;
+      io.src_ld = io.src_cols = 0;
+      io.norms_off = (int)((char*)norms - sm);
+      io.norms_done = false;
+      if (oe && !modeC) {
+        // the register path loads M itself (zero padded on the fly) and leaves s Vh in Wg: no staging copy
+        io.src = Mg;
+        io.src_ld = io.src_cols = c;
+      } else if (modeC) {
         // Wg = [ M^T 0 | I 0 ]  (c x len)
         for (int idx = tid; idx < c * len; idx += nt) {
           const int r = idx / len, cc = idx - r * len;
@@ -579,13 +589,15 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       QSP_TOCK(1);
       int nsweeps = 0;
       if (!jacobi_svd_rows(Wg, nrows, modeC ? ndotp : len, len, Wsm, P.cap_rows_elems, P.tpp, tol * tol, P.max_sweeps, red,
-                           &nsweeps))
+                           &nsweeps, &io))
         st |= QSP_ST_JACOBI_NOCONV;
       QSP_TOCK(2);
       pc[5] += nsweeps;
       pc[6] += 1;
       // ---- singular values = row norms; rank them ---------------------------------------
-      {
+      if (io.norms_done) {  // the register path left the squared norms behind
+        for (int r = tid; r < nrows; r += nt) norms[r] = sqrt(norms[r]);
+      } else {
         const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
         for (int r = warp; r < nrows; r += nw) {
           double s2 = 0.0;
