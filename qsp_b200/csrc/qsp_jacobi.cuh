@@ -20,12 +20,15 @@
 
 // One full tournament sweep over `nrows` rows of W (shared memory, row stride ldw).
 // Returns the block-wide number of rotations above QSP_JAC_QUAD (0 = converged).  All threads must call.
+// n0 > 0: bipartite sweep -- only the pairs (i, j) with i < n0 <= j (rows of two different blocks) are
+// visited, max(n0, nrows - n0) rounds of disjoint pairs; n0 = 0: all pairs (circle tournament).
 __device__ inline int jacobi_sweep_smem(cplx* W, int nrows, int ndot, int len, int ldw, int tpp, double tol2,
-                                        double* red) {
+                                        double* red, int n0 = 0) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int nteams = nt / tpp, team = tid / tpp, tl = tid % tpp;
   const int np = (nrows + 1) & ~1;  // padded to even
-  const int npairs = np / 2, nrounds = np - 1;
+  const int n1 = nrows - n0, nmax = n0 > n1 ? n0 : n1;
+  const int npairs = n0 > 0 ? nmax : np / 2, nrounds = n0 > 0 ? nmax : np - 1;
   const int passes = (npairs + nteams - 1) / nteams;
   int nrot = 0;
   for (int r = 0; r < nrounds; ++r) {
@@ -33,7 +36,12 @@ __device__ inline int jacobi_sweep_smem(cplx* W, int nrows, int ndot, int len, i
       const int pi = team + ps * nteams;
       int a = 0, b = 0;
       bool valid = pi < npairs;
-      if (valid) {
+      if (valid && n0 > 0) {
+        const int jb = (pi + r) % nmax;
+        a = pi;
+        b = n0 + jb;
+        valid = (pi < n0) && (jb < n1);
+      } else if (valid) {
         if (pi == 0) {
           a = np - 1;
           b = r;
@@ -148,6 +156,18 @@ __device__ inline bool jacobi_rows(cplx* Wg, int nrows, int ndot, int len, cplx*
     tpp = team_width(2 * rb);
     while (sweeps < max_sweeps) {
       int nrot = 0;
+      // pairs inside a block once per sweep ...
+      for (int bi = 0; bi < nblk; ++bi) {
+        const int r0 = bi * rb, n0 = imin(rb, nrows - r0);
+        if (n0 < 2) continue;
+        copy_rows(Wsm, len, Wg + (long)r0 * len, len, n0, len);
+        __syncthreads();
+        nrot += jacobi_sweep_smem(Wsm, n0, ndot, len, len, tpp, tol2, red);
+        __syncthreads();
+        copy_rows(Wg + (long)r0 * len, len, Wsm, len, n0, len);
+        __syncthreads();
+      }
+      // ... and the pairs between two blocks once per block pair
       for (int bi = 0; bi < nblk; ++bi) {
         for (int bj = bi + 1; bj < nblk; ++bj) {
           const int r0 = bi * rb, n0 = imin(rb, nrows - r0);
@@ -155,7 +175,7 @@ __device__ inline bool jacobi_rows(cplx* Wg, int nrows, int ndot, int len, cplx*
           copy_rows(Wsm, len, Wg + (long)r0 * len, len, n0, len);
           copy_rows(Wsm + (long)n0 * len, len, Wg + (long)r1 * len, len, n1, len);
           __syncthreads();
-          nrot += jacobi_sweep_smem(Wsm, n0 + n1, ndot, len, len, tpp, tol2, red);
+          nrot += jacobi_sweep_smem(Wsm, n0 + n1, ndot, len, len, tpp, tol2, red, n0);
           __syncthreads();
           copy_rows(Wg + (long)r0 * len, len, Wsm, len, n0, len);
           copy_rows(Wg + (long)r1 * len, len, Wsm + (long)n0 * len, len, n1, len);
