@@ -36,6 +36,11 @@ def lib():
 
         if not torch.cuda.is_available():
             raise QspError("qsp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if not os.path.exists(DEFAULT_LIB) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            try:  # safety net for a tree that arrives without the built library (single process only)
+                build()
+            except (OSError, subprocess.CalledProcessError) as e:
+                raise QspError(f"libqsp_b200.so is missing and could not be built: {e}") from e
         l = QspLib(DEFAULT_LIB)
         if not l.is_device_build():
             raise QspError(f"{DEFAULT_LIB} is not a device build")
