@@ -15,8 +15,9 @@
 #include "qsp_common.cuh"
 
 // A sweep whose largest rotated |g|/sqrt(alpha beta) is <= QSP_JAC_QUAD leaves off-diagonals of
-// order n * QSP_JAC_QUAD^2 ~ 1e-16 (quadratic convergence): no verification sweep is needed.
-#define QSP_JAC_QUAD 1e-9
+// order QSP_JAC_QUAD^2 ~ 1e-15 (quadratic convergence), i.e. below the rotation threshold 4e-16 sqrt(n)
+// that defines convergence anyway: no verification sweep is needed.
+#define QSP_JAC_QUAD 3e-8
 
 // One full tournament sweep over `nrows` rows of W (shared memory, row stride ldw).
 // Returns the block-wide number of rotations above QSP_JAC_QUAD (0 = converged).  All threads must call.
@@ -98,7 +99,7 @@ __device__ inline int jacobi_sweep_smem(cplx* W, int nrows, int ndot, int len, i
           xw[c] = xn;
           yw[c] = yn;
         }
-        if (tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) ++nrot;  // rotations below it leave ~1e-18: no verification sweep
+        if (tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) ++nrot;  // rotations below it leave ~1e-15: no verification sweep
       }
     }
     __syncthreads();
