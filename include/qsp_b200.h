@@ -100,6 +100,14 @@ int qsp_apply_inverse_and_compress(const qsp_c128* in, const int32_t* bonds_in, 
                                    int normalize, qsp_c128* amp0, int32_t* status, void* work, size_t work_bytes,
                                    void* stream);
 
+/* lcu/lcu.py:75,89-92: out = alpha |x> + beta |y>, the direct sum of the bond spaces
+ * (quimb MatrixProductState.__add__ / __sub__ / scalar __mul__); alpha[B], beta[B] complex, D_out >= live
+ * bond of x + live bond of y, out distinct from x and y.  qsp_mps_scale: |x> <- alpha |x> in place. */
+int qsp_mps_axpby(const qsp_c128* x, const int32_t* bonds_x, int D_x, const qsp_c128* y, const int32_t* bonds_y, int D_y,
+                  const qsp_c128* alpha, const qsp_c128* beta, qsp_c128* out, int32_t* bonds_out, int D_out, int B, int L,
+                  int32_t* status, void* stream);
+int qsp_mps_scale(qsp_c128* x, const int32_t* bonds_x, int D_x, const qsp_c128* alpha, int B, int L, void* stream);
+
 /* the gate application of apply_unitary_layer_on_wfn (core.py:126-138) on a
  * RIGHT-canonical MPS, exact; the `compress('right')` of core.py:140 is
  * qsp_left_canonize + qsp_right_compress on the result. */

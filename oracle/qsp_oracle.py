@@ -503,6 +503,112 @@ def mps_preparation_sequential(tensor_array, num_seq_layers, shape="lrp", do_com
 # --------------------------------------------------------------------------------------
 # dense checks for small L (qiskit_circuit.py:34-70)
 # --------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------
+# lcu/lcu.py: linear combination of D=2 circuits, static construction
+# --------------------------------------------------------------------------------------
+def mps_scale(mps, x):
+    """x * |mps>.  (quimb spreads the scalar over all tensors, `multiply(spread_over='all')`; only the state
+    matters here, so it goes onto site 0.)"""
+    out = copy_mps(mps)
+    out[0] = out[0] * x
+    return out
+
+
+def mps_add(m1, m2):
+    """|m1> + |m2> as the direct sum of the bond spaces (quimb MatrixProductState.__add__, lcu.py:75,89-92)."""
+    L = len(m1)
+    if L == 1:
+        return [m1[0] + m2[0]]
+    out = []
+    for i, (a, b) in enumerate(zip(m1, m2)):
+        la, _, ra = a.shape
+        lb, _, rb = b.shape
+        dt = np.result_type(a.dtype, b.dtype)
+        if i == 0:
+            t = np.zeros((1, 2, ra + rb), dt)
+            t[:, :, :ra], t[:, :, ra:] = a, b
+        elif i == L - 1:
+            t = np.zeros((la + lb, 2, 1), dt)
+            t[:la], t[la:] = a, b
+        else:
+            t = np.zeros((la + lb, 2, ra + rb), dt)
+            t[:la, :, :ra], t[la:, :, ra:] = a, b
+        out.append(t)
+    return out
+
+
+def compress_copy(psi, max_bond, completion="lapack"):
+    """lcu.py:15-27: copy; right_canonize; normalize; compress(form='right', max_bond); the D=2 unitary of it."""
+    f = copy_mps(psi)
+    right_canonize(f, normalize=True)
+    compress(f, max_bond=max_bond)
+    unitary = generate_bond_d_unitary(f, completion=completion) if max_bond == 2 else 0
+    return f, unitary
+
+
+def lcu_kappa_closed_form(p, q, A, c, F):
+    """argmax over real kappa of |p + kappa q|^2 / (A + 2 kappa Re(c) + kappa^2 F) -- the quantity lcu.py:30-31
+    hands to BFGS -- from the stationarity condition (a quadratic in kappa).  p = <psi|a>, q = <psi|f>, A = <a|a>,
+    c = <a|f>, F = <f|f>."""
+    pp, pq, qq, cr = abs(p) ** 2, (np.conj(p) * q).real, abs(q) ** 2, np.real(c)
+    # d/dk [(pp + 2 k pq + k^2 qq) / (A + 2 k cr + k^2 F)] = 0
+    a2 = qq * cr - pq * F
+    a1 = qq * A - pp * F
+    a0 = pq * A - pp * cr
+    val = lambda k: (pp + 2 * k * pq + k * k * qq) / (A + 2 * k * cr + k * k * F)
+    if abs(a2) < 1e-300:
+        roots = [-a0 / a1] if abs(a1) > 1e-300 else [0.0]
+    else:
+        disc = max(a1 * a1 - 4 * a2 * a0, 0.0)
+        sq = np.sqrt(disc)
+        roots = [(-a1 + sq) / (2 * a2), (-a1 - sq) / (2 * a2)]
+    return float(max(roots, key=val))
+
+
+def lcu_unitary_circuit(mps, italic_D=4, do_compression=False, max_bond_dim=None, overlaps_gap=4, completion="lapack",
+                        kappa_solver="bfgs"):
+    """lcu/lcu.py:32-142 (qubit_hamiltonian = 0).  kappa_solver 'bfgs' follows the reference
+    (scipy.optimize.minimize, BFGS from 0.1); 'closed' is the exact maximiser the device path uses."""
+    from scipy.optimize import minimize
+
+    mps = copy_mps(mps)
+    right_canonize(mps, normalize=True)
+    kappas, unitaries, approx_ov, overlaps, it_ds = [], [], [], [], []
+    approx = encoded = None
+    zero = cl_zero_mps(len(mps))
+    for it in range(italic_D):
+        if it == 0:
+            approx, unitary = compress_copy(mps, 2, completion)
+            kappa = 1
+            encoded = apply_unitary_layers_on_wfn([unitary], zero)
+        else:
+            renom = inner(approx, mps) / inner(approx, approx)  # (mps.H @ approx) / (approx.H @ approx)
+            residual, unitary = compress_copy(mps_add(mps, mps_scale(approx, -renom)), 2, completion)
+            if kappa_solver == "bfgs":
+                loss = lambda al: -np.abs(norm_mps_ovrlap(mps, mps_add(approx, mps_scale(residual, al[0]))))
+                kappa = float(minimize(loss, np.array([0.1]), method="BFGS").x[0])
+            else:
+                kappa = lcu_kappa_closed_form(inner(approx, mps), inner(residual, mps), inner(approx, approx).real,
+                                              inner(residual, approx), inner(residual, residual).real)
+            approx = mps_add(approx, mps_scale(residual, kappa))
+            encoded = mps_add(encoded, mps_scale(apply_unitary_layers_on_wfn([unitary], zero), kappa))
+            if do_compression:
+                right_canonize(approx)
+                compress(approx, max_bond=max_bond_dim)
+            compress(encoded)
+        kappas.append(kappa)
+        unitaries_sanity_check(unitary)
+        unitaries.append([unitary])
+        approx_ov.append(norm_mps_ovrlap(mps, approx))
+        overlap = norm_mps_ovrlap(mps, encoded)
+        if it % overlaps_gap == 0 or (it + 1) == italic_D:
+            it_ds.append(it)
+            overlaps.append(overlap)
+    return {"kappas": kappas, "unitaries": unitaries, "approx_mps_overlap": approx_ov, "it_Ds": it_ds, "depths": [],
+            "gate_counts": [], "overlaps": overlaps, "energies": [0.0] * len(overlaps), "approx_mps": approx,
+            "encoded_mps": encoded, "mps_orig": mps}
+
+
 def mps_to_dense(mps):
     """-> array of shape (2,)*L, axis i = site i."""
     t = mps[0]

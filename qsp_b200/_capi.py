@@ -30,6 +30,8 @@ _SIGNATURES = {
     "qsp_apply_inverse_layer": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "qsp_apply_inverse_and_compress_workspace_bytes": (_sz, [_i, _i, _i]),
     "qsp_apply_inverse_and_compress": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _d, _i, _p, _p, _p, _sz, _p]),
+    "qsp_mps_axpby": (_i, [_p, _p, _i, _p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "qsp_mps_scale": (_i, [_p, _p, _i, _p, _i, _i, _p]),
     "qsp_apply_forward_layer": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "qsp_overlap_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "qsp_overlap": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _p, _p, _sz, _p]),

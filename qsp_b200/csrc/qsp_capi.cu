@@ -329,6 +329,26 @@ extern "C" int qsp_apply_inverse_layer(const qsp_c128* in, const int32_t* bonds_
   return check_launch();
 }
 
+extern "C" int qsp_mps_axpby(const qsp_c128* x, const int32_t* bonds_x, int D_x, const qsp_c128* y, const int32_t* bonds_y,
+                             int D_y, const qsp_c128* alpha, const qsp_c128* beta, qsp_c128* out, int32_t* bonds_out,
+                             int D_out, int B, int L, int32_t* status, void* stream) {
+  if (!x || !bonds_x || !y || !bonds_y || !alpha || !beta || !out || !bonds_out || B <= 0 || L <= 0) return QSP_ERR_ARG;
+  if (out == x || out == y) return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  QSP_LAUNCH(k_mps_axpby, grid_for(B, 4, d), 256, 0, (qsp_stream_t)stream, (const cplx*)x, bonds_x, D_x, (const cplx*)y,
+             bonds_y, D_y, (const cplx*)alpha, (const cplx*)beta, (cplx*)out, bonds_out, D_out, B, L, status);
+  ++g_launches;
+  return check_launch();
+}
+extern "C" int qsp_mps_scale(qsp_c128* x, const int32_t* bonds_x, int D_x, const qsp_c128* alpha, int B, int L,
+                             void* stream) {
+  if (!x || !bonds_x || !alpha || B <= 0 || L <= 0) return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  QSP_LAUNCH(k_mps_scale, grid_for(B, 4, d), 128, 0, (qsp_stream_t)stream, (cplx*)x, bonds_x, D_x, (const cplx*)alpha, B, L);
+  ++g_launches;
+  return check_launch();
+}
+
 extern "C" int qsp_apply_forward_layer(const qsp_c128* in, const int32_t* bonds_in, int D_in, const qsp_c128* G,
                                        const int32_t* kind, qsp_c128* out, int32_t* bonds_out, int D_out, int B,
                                        int L, int32_t* status, void* stream) {

@@ -380,3 +380,77 @@ __global__ void __launch_bounds__(256) k_overlap(const cplx* __restrict__ a, con
     __syncthreads();
   }
 }
+
+// ----------------------------------------------------------------------------------
+// MPS linear combination (lcu/lcu.py:75,89-92: `mps - renom * approx`, `approx + kappa * residual`):
+// out = alpha |x> + beta |y> as the direct sum of the bond spaces -- site 0 concatenates along the right
+// bond (and carries the two scalars), the last site along the left bond, sites in between are block
+// diagonal; a chain of one site is the plain sum.  Elementwise, one CTA per instance.
+// ----------------------------------------------------------------------------------
+__global__ void k_mps_axpby(const cplx* __restrict__ x, const int32_t* __restrict__ bx, int Dx, const cplx* __restrict__ y,
+                            const int32_t* __restrict__ by, int Dy, const cplx* __restrict__ alpha,
+                            const cplx* __restrict__ beta, cplx* __restrict__ out, int32_t* __restrict__ bo, int Do, int B,
+                            int L, int32_t* __restrict__ status) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const long sx = (long)Dx * 2 * Dx, sy = (long)Dy * 2 * Dy, so = (long)Do * 2 * Do;
+  for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    const cplx* X = x + (long)inst * L * sx;
+    const cplx* Y = y + (long)inst * L * sy;
+    cplx* O = out + (long)inst * L * so;
+    const int32_t* bxi = bx + (long)inst * (L + 1);
+    const int32_t* byi = by + (long)inst * (L + 1);
+    int32_t* boi = bo + (long)inst * (L + 1);
+    const cplx al = alpha[inst], be = beta[inst];
+    bool bad = false;
+    for (int i = 0; i <= L; ++i) {
+      const bool edge = (i == 0 || i == L);
+      if (bxi[i] > Dx || byi[i] > Dy || (edge ? 1 : bxi[i] + byi[i]) > Do || (edge && (bxi[i] != 1 || byi[i] != 1))) bad = true;
+    }
+    if (bad) {
+      if (tid == 0 && status) status[inst] |= QSP_ST_BOND_OVERFLOW;
+      continue;
+    }
+    for (int i = 0; i < L; ++i) {
+      const int lx = bxi[i], rx = bxi[i + 1], ly = byi[i], ry = byi[i + 1];
+      const int lo = (i == 0) ? 1 : lx + ly, ro = (i == L - 1) ? 1 : rx + ry;
+      const int loff = (i == 0) ? 0 : lx, roff = (i == L - 1) ? 0 : rx;  // where the y block starts
+      const cplx* Xi = X + (long)i * sx;
+      const cplx* Yi = Y + (long)i * sy;
+      cplx* Oi = O + (long)i * so;
+      for (int idx = tid; idx < lo * 2 * ro; idx += nt) {
+        const int row = idx / ro, r = idx - row * ro;
+        const int l = row >> 1, p = row & 1;
+        cplx v = cmake(0.0, 0.0);
+        if (l < lx && r < rx) {
+          const cplx a = Xi[((long)l * 2 + p) * Dx + r];
+          v = (i == 0) ? cmul(al, a) : a;
+        }
+        const int l2 = l - loff, r2 = r - roff;
+        if (l2 >= 0 && l2 < ly && r2 >= 0 && r2 < ry) {
+          const cplx b = Yi[((long)l2 * 2 + p) * Dy + r2];
+          v = cadd(v, (i == 0) ? cmul(be, b) : b);
+        }
+        Oi[((long)l * 2 + p) * Do + r] = v;
+      }
+      if (tid == 0) {
+        boi[i] = lo;
+        boi[i + 1] = ro;
+      }
+    }
+  }
+}
+
+// |x> <- alpha |x> in place (the scalar goes onto site 0)
+__global__ void k_mps_scale(cplx* __restrict__ x, const int32_t* __restrict__ bx, int Dx, const cplx* __restrict__ alpha, int B,
+                            int L) {
+  const long sx = (long)Dx * 2 * Dx;
+  for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
+    cplx* X = x + (long)inst * L * sx;
+    const int r = bx[(long)inst * (L + 1) + 1];
+    const cplx al = alpha[inst];
+    for (int idx = threadIdx.x; idx < 2 * r; idx += blockDim.x) {
+      const int p = idx / r, rr = idx - p * r;
+      X[(long)p * Dx + rr] = cmul(al, X[(long)p * Dx + rr]);
+    }
+  }
+}

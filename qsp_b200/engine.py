@@ -105,6 +105,72 @@ class Engine:
                                     _runtime.current_stream_ptr())
         return status
 
+    # ---- unit-level operations (each one C-ABI call; used by qsp_b200.lcu) ----------------------
+    def empty_c(self, *shape):
+        return torch.empty(shape, dtype=torch.complex128, device=self.device)
+
+    def zeros_i(self, *shape):
+        return torch.zeros(shape, dtype=torch.int32, device=self.device)
+
+    def from_host(self, x):
+        return torch.from_numpy(np.ascontiguousarray(x)).to(self.device)
+
+    @staticmethod
+    def to_host(x):
+        return None if x is None else x.cpu().numpy()
+
+    @staticmethod
+    def copy(x):
+        return x.clone()
+
+    def left_canonize(self, mps, bonds):
+        B, L, D = mps.shape[0], mps.shape[1], mps.shape[2]
+        status = self.zeros_i(B)
+        nb = self.lib.qsp_left_canonize_workspace_bytes(B, L, D)
+        work = self._workspace(nb) if nb else None
+        self.lib.qsp_left_canonize(_p(mps), _p(bonds), B, L, D, _p(status), _p(work), nb, _runtime.current_stream_ptr())
+        return status
+
+    def right_compress(self, mps, bonds, Dout, max_bond=0, cutoff=CUTOFF, normalize=0, nsv=0, amp0=False):
+        B, L, Din = mps.shape[0], mps.shape[1], mps.shape[2]
+        out, bo, status = self.empty_c(B, L, Dout, 2, Dout), self.zeros_i(B, L + 1), self.zeros_i(B)
+        sv = torch.zeros((B, max(L - 1, 1), nsv), dtype=torch.float64, device=self.device) if nsv else None
+        amp = self.empty_c(B) if amp0 else None
+        nb = self.lib.qsp_right_compress_workspace_bytes(B, L, Din, Dout)
+        if nb == 0:
+            raise QspError(f"bond dimension {Din} -> {Dout} not supported by this build (QSP_ERR_UNSUPPORTED)")
+        work = self._workspace(nb)
+        self.lib.qsp_right_compress(_p(mps), _p(bonds), Din, _p(out), _p(bo), Dout, B, L, max_bond, cutoff, normalize,
+                                    _p(sv), nsv, _p(amp), _p(status), _p(work), nb, _runtime.current_stream_ptr())
+        return out, bo, status, sv, amp
+
+    def generate_unitaries(self, d2, d2b):
+        B, L = d2.shape[0], d2.shape[1]
+        G, kind, status = self.empty_c(B, L, 4, 4), self.zeros_i(B, L), self.zeros_i(B)
+        self.lib.qsp_generate_unitaries(_p(d2), _p(d2b), B, L, _p(G), _p(kind), _p(status), _runtime.current_stream_ptr())
+        return G, kind, status
+
+    def overlap(self, a, ba, b, bb):
+        """sum_x a(x) conj(b(x)) per instance (numerator of norm_mps_ovrlap(a, b), helper_routines.py:69)"""
+        B, L, Da, Db = a.shape[0], a.shape[1], a.shape[2], b.shape[2]
+        res = self.empty_c(B)
+        nb = self.lib.qsp_overlap_workspace_bytes(B, L, Da, Db)
+        work = self._workspace(nb)
+        self.lib.qsp_overlap(_p(a), _p(ba), Da, _p(b), _p(bb), Db, B, L, _p(res), _p(work), nb,
+                             _runtime.current_stream_ptr())
+        return res
+
+    def mps_axpby(self, x, bx, y, by, alpha, beta, Dout):
+        """alpha |x> + beta |y> (direct sum of the bonds); alpha, beta: complex arrays of length B"""
+        B, L = x.shape[0], x.shape[1]
+        out, bo, status = torch.zeros((B, L, Dout, 2, Dout), dtype=torch.complex128, device=self.device), self.zeros_i(B, L + 1), self.zeros_i(B)
+        self.lib.qsp_mps_axpby(_p(x), _p(bx), x.shape[2], _p(y), _p(by), y.shape[2], _p(alpha), _p(beta), _p(out), _p(bo),
+                               Dout, B, L, _p(status), _runtime.current_stream_ptr())
+        return out, bo, status
+
+    def mps_scale(self, x, bx, alpha):
+        self.lib.qsp_mps_scale(_p(x), _p(bx), x.shape[2], _p(alpha), x.shape[0], x.shape[1], _runtime.current_stream_ptr())
+
     # ---- the layer loop ---------------------------------------------------------------------
     def seq_prepare(self, target, bonds, layers, max_bond=0, cutoff=CUTOFF, overlaps_gap=4, second_pass=False,
                     encoded=True, want_final=False, chunk=None):

@@ -65,6 +65,29 @@ class MPSPreparation:
               f"n_gates={circ.size()}, n_2qg={circ.num_nonlocal_gates()}\n")
         return overlap, circ
 
+    def lcu_unitary_circuit(self, num_lcu_layers, verbose=False):
+        """tsp.py:287-352: the target as a linear combination of num_lcu_layers D=2 circuits.  Returns
+        (overlap, circ); the tensor part runs on the device (qsp_b200.lcu), the ancilla-controlled LCU circuit
+        (q_circs.lcu_circuit_from_unitary_layers) is not emitted by this package: circ is None and
+        self.lcu_data carries kappas and unitaries for it."""
+        from .lcu import lcu_unitary_circuit
+
+        if self.phys_dim != 2:
+            raise ValueError("only supports mps with physical dimesnion=2")
+        k = np.log2(num_lcu_layers)
+        if np.abs(k - int(k)) > 1e-12:
+            raise ValueError(f"required num_var_lcu_layers={num_lcu_layers} not a positive power of 2")
+        print(f"preparing mps as linear combination of unitaries (num_lcu_layers={num_lcu_layers})...")
+        data = lcu_unitary_circuit(self.target_mps, num_lcu_layers, verbose=verbose, engine=self._engine)
+        self.lcu_data = data
+        # tsp.py:322-333 rebuilds sum_k kappa_k U_k|0..0> and takes norm_mps_ovrlap(encoded, target): the conjugate
+        # of the last entry of data['overlaps'] (= norm_mps_ovrlap(target, encoded), evaluated on the device)
+        overlap = np.conj(data["overlaps"][-1])
+        self.lcu_data["circ"] = None
+        print(f"overllap after lcu. preparation = {np.abs(overlap):.8f}, n_gates=n/a, n_2qg=n/a (LCU circuit emission "
+              "is outside this package)\n")
+        return overlap, None
+
     def _encoded_overlap(self, unitaries):
         from .mps import gs_lst_to_gates
 

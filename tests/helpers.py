@@ -220,6 +220,23 @@ class HostDriver:
         self.sync()
         return res
 
+    def copy(self, x):
+        return x.clone() if hasattr(x, "clone") else x.copy()
+
+    def mps_axpby(self, x, bx, y, by, alpha, beta, Dout):
+        B, L = x.shape[0], x.shape[1]
+        out = self.empty_c(B, L, Dout, 2, Dout)
+        bo = self.zeros_i(B, L + 1)
+        status = self.zeros_i(B)
+        self.lib.qsp_mps_axpby(self.p(x), self.p(bx), x.shape[2], self.p(y), self.p(by), y.shape[2], self.p(alpha),
+                               self.p(beta), self.p(out), self.p(bo), Dout, B, L, self.p(status), self.stream)
+        self.sync()
+        return out, bo, status
+
+    def mps_scale(self, x, bx, alpha):
+        self.lib.qsp_mps_scale(self.p(x), self.p(bx), x.shape[2], self.p(alpha), x.shape[0], x.shape[1], self.stream)
+        self.sync()
+
     def prepare_target(self, arr, bonds, cutoff=1e-10):
         B, L, D = arr.shape[0], arr.shape[1], arr.shape[2]
         status = self.zeros_i(B)
