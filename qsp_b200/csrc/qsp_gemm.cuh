@@ -130,7 +130,9 @@ __device__ inline void cta_zgemm(int m, int n, int kdim, const cplx* __restrict_
 
 // Deeper k-tiles (half the barriers and exposed load latencies per flop) for kernels that can
 // spare the shared memory: qsp_gemm_smem_bytes(nt, QSP_GEMM_TK_DEEP).
+#ifndef QSP_GEMM_TK_DEEP
 #define QSP_GEMM_TK_DEEP 16
+#endif
 __device__ inline void cta_zgemm_deep(int m, int n, int kdim, const cplx* __restrict__ A, long sAr, long sAk, bool conjA,
                                       const cplx* __restrict__ B, long sBk, long sBc, bool conjB, cplx* __restrict__ C,
                                       long sCr, long sCc, bool accumulate, cplx* tiles) {

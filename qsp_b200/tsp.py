@@ -144,6 +144,20 @@ class BatchedMPSPreparation:
                                    f"status {int(res.status[bad[0]]):#x} (QSP_ST_* in include/qsp_b200.h)")
         return res.overlaps[num_seq_layers - 1], res
 
+    def lcu_unitary_circuit(self, num_lcu_layers, do_compression=False, max_bond_dim=None, overlaps_gap=4, check=False):
+        """Batched lcu_unitary_circuit (lcu/lcu.py:32-142): returns (overlaps[B] of the encoded states, dict of host
+        arrays -- kappas[terms, B], G[terms, B, L, 4, 4], kind, approx_mps_overlap, overlaps, it_Ds, status[B])."""
+        from .lcu import lcu_unitary_circuit_batched
+
+        r = lcu_unitary_circuit_batched(self.engine, self.mps, self.bonds, num_lcu_layers, do_compression, max_bond_dim,
+                                        overlaps_gap)
+        self.lcu_data = r
+        if check and r["status"].any():
+            bad = np.nonzero(r["status"])[0]
+            raise RuntimeError(f"{bad.size} of {self.B} instances failed, first: instance {int(bad[0])} "
+                               f"status {int(r['status'][bad[0]]):#x} (QSP_ST_* in include/qsp_b200.h)")
+        return r["overlaps"][-1], r
+
     def unitaries(self, b):
         """Reference-style list of Gs_lst layers for instance b."""
         G = self.seq_data.G[:, b].cpu().numpy()

@@ -106,6 +106,18 @@ def test_lcu_on_the_gpu():
 
 
 @pytest.mark.gpu
+def test_lcu_batched_api():
+    from qsp_b200.tsp import BatchedMPSPreparation
+
+    raw = [O.readme_mps(8, 3, s) for s in range(3)]
+    bp = BatchedMPSPreparation(raw, shape="lrp")
+    ov, r = bp.lcu_unitary_circuit(4, check=True)
+    for k, a in enumerate(raw):
+        ref = O.lcu_unitary_circuit(O.prepare_target(a, "lrp"), 4, completion="canonical", kappa_solver="closed")
+        assert abs(ov[k] - ref["overlaps"][-1]) < 1e-10 and np.abs(r["kappas"][:, k] - ref["kappas"]).max() < 1e-9
+
+
+@pytest.mark.gpu
 def test_lcu_facade(capsys):
     from qsp_b200.tsp import MPSPreparation
 
