@@ -35,19 +35,28 @@ def lcu_kappa(p, q, A, c, F):
     return np.where(np.isfinite(k), k, 0.0)
 
 
+def _safe_inv_sqrt(v, tiny=1e-24):
+    return np.where(v > tiny, 1.0 / np.sqrt(np.maximum(v, tiny)), 0.0).astype(np.complex128)
+
+
 def _d2_term(ops, x, xb, cutoff):
     """compress_copy(x, 2) (lcu.py:15-27): f = D=2 truncation of x/||x|| (not renormalised), fn = f/||f||, and the
-    unitary layer of fn (generate_bond_d_unitary).  x is left-canonised in place."""
+    unitary layer of fn (generate_bond_d_unitary).  x is left-canonised in place.  Instances whose x vanishes (the
+    target is already reproduced exactly; the reference divides by zero there) come back as `dead`: f = fn = 0, their
+    kappa will be 0 and their status bits are dropped."""
     h = ops.to_host
     n2 = h(ops.overlap(x, xb, x, xb)).real
+    dead = ~(n2 > 1e-24)
     st = h(ops.left_canonize(x, xb))
     f, fb, st2, _, _ = ops.right_compress(x, xb, 2, max_bond=2, cutoff=cutoff, normalize=0)
-    ops.mps_scale(f, fb, ops.from_host((1.0 / np.sqrt(n2)).astype(np.complex128)))
+    ops.mps_scale(f, fb, ops.from_host(_safe_inv_sqrt(n2)))
     t2 = h(ops.overlap(f, fb, f, fb)).real
+    t2 = np.where(dead, 0.0, t2)
     fn = ops.copy(f)
-    ops.mps_scale(fn, fb, ops.from_host((1.0 / np.sqrt(t2)).astype(np.complex128)))
+    ops.mps_scale(fn, fb, ops.from_host(_safe_inv_sqrt(t2)))
     G, kind, st3 = ops.generate_unitaries(fn, fb)
-    return f, fb, fn, G, kind, t2, st | h(st2) | h(st3)
+    st = np.where(dead, 0, st | h(st2) | h(st3)).astype(np.int32)
+    return f, fb, fn, G, kind, t2, st, dead
 
 
 def lcu_unitary_circuit_batched(ops, psi, pb, italic_D=4, do_compression=False, max_bond_dim=None, overlaps_gap=4,
@@ -68,18 +77,18 @@ def lcu_unitary_circuit_batched(ops, psi, pb, italic_D=4, do_compression=False, 
     approx = ab = enc = eb = None
     for it in range(italic_D):
         if it == 0:
-            f, fb, fn, G, kind, t2, st = _d2_term(ops, ops.copy(psi), ops.copy(pb), cutoff)
+            f, fb, fn, G, kind, t2, st, dead = _d2_term(ops, ops.copy(psi), ops.copy(pb), cutoff)
             kappa = np.ones(B)
             approx, ab, enc, eb = f, fb, fn, ops.copy(fb)
         else:
             p = h(ops.overlap(approx, ab, psi, pb))  # <a|psi> ... (mps.H @ approx), lcu.py:74
             A = h(ops.overlap(approx, ab, approx, ab)).real
             x, xb, st0 = ops.mps_axpby(psi, pb, approx, ab, one, cvec(-p / A), D + approx.shape[2])
-            f, fb, fn, G, kind, t2, st = _d2_term(ops, x, xb, cutoff)
+            f, fb, fn, G, kind, t2, st, dead = _d2_term(ops, x, xb, cutoff)
             st = st | h(st0)
             q = h(ops.overlap(f, fb, psi, pb))
             c = h(ops.overlap(f, fb, approx, ab))
-            kappa = lcu_kappa(p, q, A, c, t2)
+            kappa = np.where(dead, 0.0, lcu_kappa(p, q, A, np.where(dead, 0.0, c), t2))
             approx, ab, st1 = ops.mps_axpby(approx, ab, f, fb, one, cvec(kappa), approx.shape[2] + 2)
             enc, eb, st2 = ops.mps_axpby(enc, eb, fn, fb, one, cvec(kappa), enc.shape[2] + 2)
             st = st | h(st1) | h(st2)

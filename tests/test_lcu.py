@@ -4,7 +4,7 @@ through the C ABI and the facade."""
 import numpy as np
 import pytest
 
-from helpers import HostDriver, gates_to_layers, pack_batch, unpack_batch
+from helpers import HostDriver, edge_cases, gates_to_layers, pack_batch, unpack_batch
 from oracle import qsp_oracle as O
 from qsp_b200.lcu import lcu_kappa, lcu_unitary_circuit_batched
 
@@ -75,6 +75,25 @@ def test_lcu_on_the_emulated_kernels():
     tgs = [_prepared(O.random_mps(6, 4, 20 + s)) for s in range(2)]
     _check_lcu(drv, tgs, 4)
     _check_lcu(drv, tgs[:1], 4, do_compression=True, max_bond_dim=4)
+
+
+@pytest.mark.parametrize("name", list(edge_cases()))
+def test_lcu_edge_cases_on_the_emulator(name):
+    """targets that the first D=2 term already reproduces (bond <= 2, product states, one or two sites): the
+    residual vanishes, where the reference divides by zero; here the further terms get kappa = 0 and nothing is NaN."""
+    import warnings
+
+    mps = edge_cases()[name][0]
+    t = _prepared(mps)
+    a, b = pack_batch([t])
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        r = lcu_unitary_circuit_batched(HostDriver(), a, b, 3)
+    assert r["status"].max() == 0 and np.isfinite(r["overlaps"]).all() and np.isfinite(r["kappas"]).all()
+    if max(O.bonds_of(t)) <= 2:
+        assert np.allclose(r["kappas"][:, 0], [1, 0, 0]) and abs(abs(r["overlaps"][-1, 0]) - 1) < 1e-12
+    else:
+        assert abs(r["overlaps"][-1, 0]) > abs(r["overlaps"][0, 0])
 
 
 def test_mps_axpby_kernel_on_the_emulator():
