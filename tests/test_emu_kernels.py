@@ -101,7 +101,15 @@ def _jacobi_cases(nrows, ncols, seed=3):
     graded = g(nrows, ncols) * np.logspace(0, -9, ncols)     # graded columns (the carried U s)
     dup = full.copy(); dup[1] = dup[0]; dup[5] = 2 * dup[4]  # exactly dependent rows
     zero = full.copy(); zero[2] = 0                          # a zero row
-    return {"full": full, "rank3": low, "graded": graded, "duplicates": dup, "zero_row": zero}
+    # clustered singular values (relative gaps 1e-6 and 1e-9): the quadratic-convergence stop must not leave the
+    # near-degenerate directions mixed
+    k = min(nrows, ncols)
+    u, _ = np.linalg.qr(g(nrows, k))
+    v, _ = np.linalg.qr(g(ncols, k))
+    sv = 1.0 + 1e-6 * np.arange(k)
+    sv[k // 2:] = 0.5 + 1e-9 * np.arange(k - k // 2)
+    clustered = (u * sv) @ v.conj().T
+    return {"full": full, "rank3": low, "graded": graded, "duplicates": dup, "zero_row": zero, "clustered": clustered}
 
 
 @pytest.mark.parametrize("nrows,ldw,nt", [(16, 128, 64), (15, 128, 64), (8, 64, 64)])
