@@ -11,6 +11,7 @@ What it is: a numpy/scipy restatement, step for step, of
     qsp/sequential/core.py:12-141, 217-270              D=2 truncation, unitaries, (inverse) layer application
     qsp/tsp_helper_routines/helper_routines.py:29-73    zero state, normalised overlap, specs, sanity check
     qsp/q_circs/qiskit_circuit.py:34-70                 gate ordering / endianness of the emitted circuit
+    qsp/lcu/lcu.py:15-142                               LCU static construction (MPS sums as direct sums)
 
 The arithmetic of that path lives in quimb (requirements.txt:4, un-pinned, 1.4-1.6 era
 judging from the pickles), which is NOT installed here and cannot be (no network); the
@@ -27,7 +28,9 @@ pickles come from an older revision with an unknown bond bound).  From layer 2 o
 reference's absolute numbers depend on which null-space basis LAPACK returns
 (core.py:39,59,90) and are not reproducible across platforms: ABSOLUTE PARITY FOR
 LAYERS >= 2 IS UNPINNED by anything the reference ships; it is pinned conditionally
-(teacher forcing, same-convention `completion='canonical'`) -- see DESIGN.md.
+(teacher forcing, same-convention `completion='canonical'`) -- see DESIGN.md.  The LCU restatement is
+PARITY UNPINNED beyond its first term (= layer 1 of the sequential path): the reference ships no usable LCU
+fixture (AKLT degenerate, random unseeded, N2 input missing).
 
 An MPS is a python list of L arrays shaped (l, 2, r), l = 1 at site 0, r = 1 at site L-1
 (the reference keeps the end tensors 2-D; with size-1 dummy legs every reshape in
