@@ -235,7 +235,85 @@ __device__ __noinline__ void cta_householder_qr_t(cplx* S, int m, int n, int ldS
   __syncthreads();
   pc[2] += qsp_clock() - tck, tck = qsp_clock();
   // ---- thin Q in place (zung2r) ---------------------------------------------------------
-  for (int j = K - 1; j >= 0; --j) {
+  int jtop = K - 1;
+  if (MAXR <= 4) {
+    // Two reflectors per pass while the registers allow: H_{j-1} H_j a = a - tau_j w1 v_j - tau_{j-1} (w0 - tau_j z w1) v_{j-1}
+    // with w1 = v_j^H a, w0 = v_{j-1}^H a, z = v_{j-1}^H v_j -- the two dot products of a column are independent,
+    // a column is read and written once per pair, and a pair costs two barriers instead of four.
+    for (; jtop >= 1; jtop -= 2) {
+      const int j = jtop, b0 = j - 1;  // rows b0 .. m-1 are touched
+      cplx* colj = S + (long)j * ldS;
+      cplx* colp = S + (long)(j - 1) * ldS;
+      const cplx tj = tau[j], tp = tau[j - 1];
+      cplx vj[MAXR], vp[MAXR];
+      cplx z = cmake(0.0, 0.0);
+#pragma unroll
+      for (int k = 0; k < MAXR; ++k) {
+        const int r = b0 + lane + 32 * k;
+        vj[k] = (r == j) ? cmake(1.0, 0.0) : ((r > j && r < m) ? colj[r] : cmake(0.0, 0.0));
+        vp[k] = (r == b0) ? cmake(1.0, 0.0) : ((r > b0 && r < m) ? colp[r] : cmake(0.0, 0.0));
+        cfma_conja(z, vp[k], vj[k]);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        z.x += shfl_xor_d(z.x, o);
+        z.y += shfl_xor_d(z.y, o);
+      }
+      const cplx tz = cmul(tj, z);
+      __syncthreads();  // every warp holds both reflectors: their columns may now be overwritten
+      for (int c = j + 1 + warp; c < K; c += nw) {
+        cplx* col = S + (long)c * ldS;
+        cplx a[MAXR];
+        cplx w1 = cmake(0.0, 0.0), w0 = cmake(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+          const int r = b0 + lane + 32 * k;
+          a[k] = (r < m) ? col[r] : cmake(0.0, 0.0);
+          cfma_conja(w1, vj[k], a[k]);
+          cfma_conja(w0, vp[k], a[k]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          w1.x += shfl_xor_d(w1.x, o);
+          w1.y += shfl_xor_d(w1.y, o);
+          w0.x += shfl_xor_d(w0.x, o);
+          w0.y += shfl_xor_d(w0.y, o);
+        }
+        const cplx g1 = cmul(tj, w1);
+        const cplx g0 = cmul(tp, csub(w0, cmul(tz, w1)));
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+          const int r = b0 + lane + 32 * k;
+          if (r < m) col[r] = csub(csub(a[k], cmul(g1, vj[k])), cmul(g0, vp[k]));
+        }
+      }
+      if (warp == nw - 1) {
+        // column j = H_{j-1} H_j e_j (w1 = 1, w0 = conj(v_{j-1}[j])), column j-1 = H_{j-1} e_{j-1}; sign-fixed like R
+        const double sj = beta[j] < 0.0 ? -1.0 : 1.0, sp = beta[j - 1] < 0.0 ? -1.0 : 1.0;
+        cplx vpj = cmake(0.0, 0.0);  // v_{j-1}[j]: lane 1, k = 0 holds it
+        {
+          const cplx mine = vp[0];
+          vpj.x = __shfl_sync(QSP_FULL_MASK, mine.x, 1);
+          vpj.y = __shfl_sync(QSP_FULL_MASK, mine.y, 1);
+        }
+        const cplx g0 = cmul(tp, csub(cconj(vpj), tz));
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+          const int r = b0 + lane + 32 * k;
+          if (r < m) {
+            cplx ej = (r == j) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+            cplx ep = (r == b0) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+            colj[r] = cscale(csub(csub(ej, cmul(tj, vj[k])), cmul(g0, vp[k])), sj);
+            colp[r] = cscale(csub(ep, cmul(tp, vp[k])), sp);
+          }
+        }
+        for (int r = lane; r < b0; r += 32) {
+          colj[r] = cmake(0.0, 0.0);
+          colp[r] = cmake(0.0, 0.0);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = jtop; j >= 0; --j) {
     cplx* colj = S + (long)j * ldS;
     const cplx tj = tau[j];
     if (tj.x != 0.0 || tj.y != 0.0) {
