@@ -35,7 +35,12 @@ def lcu_kappa(p, q, A, c, F):
     return np.where(np.isfinite(k), k, 0.0)
 
 
-def _safe_inv_sqrt(v, tiny=1e-24):
+# <x|x> of a difference of two O(1) states is only known to ~1e-15 absolute (transfer-matrix contraction of the
+# direct sum), so a residual is called exhausted below this norm^2 (fidelity of the approximation > 1 - 1e-12)
+DEAD_NORM2 = 1e-12
+
+
+def _safe_inv_sqrt(v, tiny=DEAD_NORM2):
     return np.where(v > tiny, 1.0 / np.sqrt(np.maximum(v, tiny)), 0.0).astype(np.complex128)
 
 
@@ -46,7 +51,7 @@ def _d2_term(ops, x, xb, cutoff):
     kappa will be 0 and their status bits are dropped."""
     h = ops.to_host
     n2 = h(ops.overlap(x, xb, x, xb)).real
-    dead = ~(n2 > 1e-24)
+    dead = ~(n2 > DEAD_NORM2)
     st = h(ops.left_canonize(x, xb))
     f, fb, st2, _, _ = ops.right_compress(x, xb, 2, max_bond=2, cutoff=cutoff, normalize=0)
     ops.mps_scale(f, fb, ops.from_host(_safe_inv_sqrt(n2)))
