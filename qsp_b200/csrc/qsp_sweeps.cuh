@@ -186,7 +186,115 @@ __device__ __noinline__ void cta_householder_qr_t(cplx* S, int m, int n, int ldS
   const int K = imin(m, n);
   if (warp == 0) qr_make_reflector(S, 0, m, lane, tau, beta);
   __syncthreads();
-  for (int j = 0; j < K; ++j) {
+  int jstart = 0;
+  if (MAXR <= 4 && nw > 1 && K >= 2) {
+    // Two reflectors per pass (registers allow it up to 128 rows): with z = v_{j+1}^H v_j,
+    //   H_{j+1}^H H_j^H a = a - f0 w0 v_j - f1 (u1 - f0 z w0) v_{j+1},  w0 = v_j^H a,  u1 = v_{j+1}^H a,  f = conj(tau).
+    // Warp 0 looks two reflectors ahead (columns j+2, j+3), the other warps share the columns from j+4 on;
+    // one barrier per pair.
+    if (warp == 0) {  // reflector 1: H_0^H on column 1, then build it
+      cplx v0[MAXR];
+      const cplx t0 = tau[0];
+#pragma unroll
+      for (int k = 0; k < MAXR; ++k) {
+        const int r = lane + 32 * k;
+        v0[k] = (r == 0) ? cmake(1.0, 0.0) : (r < m ? S[r] : cmake(0.0, 0.0));
+      }
+      qr_apply_reflector(v0, S + ldS, 0, m, lane, cconj(t0));
+      __syncwarp();
+      qr_make_reflector(S + ldS, 1, m, lane, tau, beta);
+    }
+    __syncthreads();
+    int j = 0;
+    for (; j + 1 < K; j += 2) {
+      const cplx* colj = S + (long)j * ldS;
+      const cplx* colq = S + (long)(j + 1) * ldS;
+      const cplx f0 = cconj(tau[j]), f1 = cconj(tau[j + 1]);
+      cplx vj[MAXR], vq[MAXR];
+      cplx z = cmake(0.0, 0.0);
+#pragma unroll
+      for (int k = 0; k < MAXR; ++k) {
+        const int r = j + lane + 32 * k;
+        vj[k] = (r == j) ? cmake(1.0, 0.0) : (r < m ? colj[r] : cmake(0.0, 0.0));
+        vq[k] = (r == j + 1) ? cmake(1.0, 0.0) : ((r > j + 1 && r < m) ? colq[r] : cmake(0.0, 0.0));
+        cfma_conja(z, vq[k], vj[k]);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        z.x += shfl_xor_d(z.x, o);
+        z.y += shfl_xor_d(z.y, o);
+      }
+      const cplx f0z = cmul(f0, z);
+      auto pair_apply = [&](cplx* col) {
+        cplx a[MAXR];
+        cplx w0 = cmake(0.0, 0.0), u1 = cmake(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+          const int r = j + lane + 32 * k;
+          a[k] = (r < m) ? col[r] : cmake(0.0, 0.0);
+          cfma_conja(w0, vj[k], a[k]);
+          cfma_conja(u1, vq[k], a[k]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          w0.x += shfl_xor_d(w0.x, o);
+          w0.y += shfl_xor_d(w0.y, o);
+          u1.x += shfl_xor_d(u1.x, o);
+          u1.y += shfl_xor_d(u1.y, o);
+        }
+        const cplx g0 = cmul(f0, w0);
+        const cplx g1 = cmul(f1, csub(u1, cmul(f0z, w0)));
+#pragma unroll
+        for (int k = 0; k < MAXR; ++k) {
+          const int r = j + lane + 32 * k;
+          if (r < m) col[r] = csub(csub(a[k], cmul(g0, vj[k])), cmul(g1, vq[k]));
+        }
+      };
+      if (warp == 0) {
+        if (j + 2 < n) {
+          cplx* c2 = S + (long)(j + 2) * ldS;
+          pair_apply(c2);
+          if (j + 2 < K) {
+            __syncwarp();
+            qr_make_reflector(c2, j + 2, m, lane, tau, beta);
+          }
+        }
+        if (j + 3 < n) {
+          cplx* c3 = S + (long)(j + 3) * ldS;
+          pair_apply(c3);
+          if (j + 3 < K) {  // H_{j+2}^H as well, then reflector j+3 (otherwise the tail below applies H_{j+2})
+            __syncwarp();
+            const cplx* c2 = S + (long)(j + 2) * ldS;
+            cplx v2[MAXR];
+#pragma unroll
+            for (int k = 0; k < MAXR; ++k) {
+              const int r = j + 2 + lane + 32 * k;
+              v2[k] = (r == j + 2) ? cmake(1.0, 0.0) : (r < m ? c2[r] : cmake(0.0, 0.0));
+            }
+            qr_apply_reflector(v2, c3, j + 2, m, lane, cconj(tau[j + 2]));
+            __syncwarp();
+            qr_make_reflector(c3, j + 3, m, lane, tau, beta);
+          }
+        }
+      } else {
+        for (int c = j + 4 + (warp - 1); c < n; c += nw - 1) pair_apply(S + (long)c * ldS);
+      }
+      __syncthreads();
+    }
+    jstart = j;  // K odd: reflector K-1 exists but has not been applied to the columns behind it
+    if (jstart < K) {
+      const cplx* colj = S + (long)jstart * ldS;
+      const cplx tj = tau[jstart];
+      cplx vr[MAXR];
+#pragma unroll
+      for (int k = 0; k < MAXR; ++k) {
+        const int r = jstart + lane + 32 * k;
+        vr[k] = (r == jstart) ? cmake(1.0, 0.0) : (r < m ? colj[r] : cmake(0.0, 0.0));
+      }
+      if (tj.x != 0.0 || tj.y != 0.0) qr_apply_columns(vr, S, ldS, jstart + 1 + warp, nw, n, jstart, m, lane, cconj(tj));
+      __syncthreads();
+    }
+    jstart = K;
+  }
+  for (int j = jstart; j < K; ++j) {
     const cplx* colj = S + (long)j * ldS;
     const cplx tj = tau[j];
     cplx vr[MAXR];
