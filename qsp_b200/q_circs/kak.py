@@ -11,7 +11,8 @@ where (a, b, c) are Weyl (KAK) coordinates of U, exp(i(a XX + b YY + c ZZ)) bein
 equivalent to W for t1 = -2a - pi/2, t2 = -2b - pi/2, t3 = 2c - pi/2, and the local factors follow
 from the magic-basis eigenvectors of U^T U and W^T W (both are diagonalised by REAL orthogonal
 matrices; mapping one eigenbasis onto the other gives A2 (x) B2, the rest is A1 (x) B1).  Product
-unitaries are emitted without any CNOT.  Host-side numpy: circuit emission stays in Python, as in
+unitaries are emitted without any CNOT, the CNOT class with one, unitaries whose m^T m has a real trace
+with two (template CX . (Rx (x) Rz) . CX) -- the minimal counts.  Host-side numpy: circuit emission stays in Python, as in
 the reference; the tensor path never calls this.
 """
 import itertools
@@ -160,6 +161,65 @@ def three_cx_core(a, b, c):
     return w[0], (float(t1[0]), float(t2[0]), float(t3[0]))
 
 
+def rx(t):
+    c, s_ = np.cos(t / 2), np.sin(t / 2)
+    return np.array([[c, -1j * s_], [-1j * s_, c]], dtype=np.complex128)
+
+
+def _locals_to_template(u, w, rng, tol=1e-9):
+    """(phase, a1, b1, a2, b2) with u = phase (a1 (x) b1) w (a2 (x) b2), or None when w is not locally equivalent
+    to u (the spectra of m^T m in the magic basis differ).  One gate; used for the 0/1/2-CNOT templates."""
+    us, phu = _su4(u[None])
+    ws, phw = _su4(w[None])
+    up, wp = _MAGIC.conj().T @ us @ _MAGIC, _MAGIC.conj().T @ ws @ _MAGIC
+    lu, p = _diag_symmetric_unitary(np.swapaxes(up, 1, 2) @ up, rng)
+    best = None
+    for k in (0, 1):
+        wk = wp * (1j ** k)
+        lw, q = _diag_symmetric_unitary(np.swapaxes(wk, 1, 2) @ wk, rng)
+        for perm in _PERMS:
+            e = np.abs(lu[0] - lw[0][perm]).max()
+            if best is None or e < best[0]:
+                best = (e, k, perm, q[0], wk[0])
+    e, k, perm, q, wk = best
+    if e > tol:
+        return None
+    q, p0 = q[:, perm], p[0].copy()
+    if np.linalg.det(q) * np.linalg.det(p0) < 0:
+        p0[:, 0] *= -1
+    o2 = q @ p0.T
+    o1 = up[0] @ o2.T @ wk.conj().T
+    l1, l2 = _MAGIC @ o1.real @ _MAGIC.conj().T, _MAGIC @ o2 @ _MAGIC.conj().T
+    a1, b1, p1, r1 = _kron_factor(l1[None])
+    a2, b2, p2, r2 = _kron_factor(l2[None])
+    return complex(phu[0] / phw[0] * (1j ** k) * p1[0] * p2[0]), a1[0], b1[0], a2[0], b2[0]
+
+
+def _fewer_cnots(u, lam, rng):
+    """Op list with one or two CNOTs when the unitary allows it (Shende-Bullock-Markov: two CNOTs suffice iff the
+    trace of m^T m is real, one iff its spectrum is {i, i, -i, -i}), else None.  lam: spectrum of m^T m."""
+    for sgn in (1.0, -1.0):  # det^{1/4} leaves the overall sign of the spectrum open
+        mu = sgn * lam
+        if np.abs(np.sort_complex(np.round(mu, 9)) - np.sort_complex(np.round(np.conj(mu), 9))).max() > 1e-7:
+            continue
+        if np.abs(mu * mu + 1.0).max() < 1e-9 and abs(mu.sum()) < 1e-9:  # locally a CNOT
+            r = _locals_to_template(u, _CX, rng)
+            if r is not None:
+                ph, a1, b1, a2, b2 = r
+                return ph, [("u", 0, a2), ("u", 1, b2), ("cx", 0, 1), ("u", 0, a1), ("u", 1, b1)]
+        th = np.sort(np.abs(np.angle(mu)))  # {t2, t2, t1, t1}: 2(a+c) = t2, 2(a-c) = t1
+        t2, t1 = 0.5 * (th[0] + th[1]), 0.5 * (th[2] + th[3])
+        a, c = (t1 + t2) / 4, (t2 - t1) / 4
+        for aa, cc in ((a, c), (a, -c), (np.pi / 2 - a, c), (np.pi / 2 - a, -c)):
+            w = _CX @ np.kron(rx(2 * aa), rz(2 * cc)) @ _CX
+            r = _locals_to_template(u, w, rng)
+            if r is not None:
+                ph, a1, b1, a2, b2 = r
+                return ph, [("u", 0, a2), ("u", 1, b2), ("cx", 0, 1), ("u", 0, rx(2 * aa)), ("u", 1, rz(2 * cc)), ("cx", 0, 1),
+                            ("u", 0, a1), ("u", 1, b1)]
+    return None
+
+
 def decompose_two_qubit_batch(u, rng=None):
     """u[n] (4x4 unitaries on kron(left, right)) -> dict of arrays:
     product[n] (bool: no CNOT needed), phase[n], a2, b2 (first one-qubit gates, left / right), t1, t2, t3
@@ -175,12 +235,19 @@ def decompose_two_qubit_batch(u, rng=None):
     out["product"] = prod
     out["a2"][prod], out["b2"][prod], out["phase"][prod] = a0[prod], b0[prod], ph0[prod]
     idx = np.nonzero(~prod)[0]
+    out["special"] = {}
     if idx.size == 0:
         return out
     v = u[idx]
     us, phu = _su4(v)
     up = _MAGIC.conj().T @ us @ _MAGIC
     lu, p = _diag_symmetric_unitary(np.swapaxes(up, 1, 2) @ up, rng)
+    # special unitaries (never the generic gates of the path): one or two CNOTs, handled one by one
+    for i in np.nonzero(np.abs(lu.sum(axis=1).imag) < 1e-9)[0]:
+        r = _fewer_cnots(v[i], lu[i], rng)
+        if r is not None:
+            out["special"][int(idx[i])] = r
+            out["phase"][idx[i]] = r[0]
     a, b, c = _weyl_from_spectrum(up, lu, p)
     w, t1, t2, t3 = _core_batch(a, b, c)
     ws, phw = _su4(w)
@@ -213,7 +280,8 @@ def decompose_two_qubit_batch(u, rng=None):
     a2, b2, p2, _ = _kron_factor(l2)
     out["a1"][idx], out["b1"][idx], out["a2"][idx], out["b2"][idx] = a1, b1, a2, b2
     out["t1"][idx], out["t2"][idx], out["t3"][idx] = t1, t2, t3
-    out["phase"][idx] = phu / phw * (1j ** best_k) * p1 * p2
+    gen = np.array([int(i) not in out["special"] for i in idx])
+    out["phase"][idx[gen]] = (phu / phw * (1j ** best_k) * p1 * p2)[gen]
     return out
 
 
@@ -222,6 +290,8 @@ def ops_from_batch(dec, i):
     side 0 = left / 1 = right factor, and ("cx", control_side, target_side)."""
     if dec["product"][i]:
         return [("u", 0, dec["a2"][i]), ("u", 1, dec["b2"][i])]
+    if int(i) in dec.get("special", {}):
+        return dec["special"][int(i)][1]
     return [("u", 0, dec["a2"][i]), ("u", 1, dec["b2"][i]), ("cx", 0, 1), ("u", 0, ry(dec["t2"][i])), ("u", 1, rz(dec["t1"][i])),
             ("cx", 1, 0), ("u", 0, ry(dec["t3"][i])), ("cx", 0, 1), ("u", 0, dec["a1"][i]), ("u", 1, dec["b1"][i])]
 

@@ -35,7 +35,22 @@ def test_special_two_qubit_gates(name):
     ph, ops = kak.decompose_two_qubit(u)
     assert np.abs(ph * kak.ops_to_matrix(ops) - u).max() < 1e-10
     ncx = sum(1 for o in ops if o[0] == "cx")
-    assert ncx == (0 if name in ("identity", "product", "phase_times_identity") else 3)
+    # minimal CNOT counts (Shende-Bullock-Markov): products 0, CNOT class 1, real trace of m^T m 2, else 3
+    want = {"identity": 0, "product": 0, "phase_times_identity": 0, "cx": 1, "xc": 1, "cz": 1, "cphase": 2, "swap_cx": 2}
+    assert ncx == want.get(name, 3)
+
+
+def test_two_cnot_class():
+    from scipy.linalg import expm
+
+    X, Y, Z = np.array([[0, 1], [1, 0]], complex), np.array([[0, -1j], [1j, 0]]), np.diag([1.0, -1.0]).astype(complex)
+    u2 = lambda s: unitary_group.rvs(2, random_state=s)
+    for k, (a, b, c) in enumerate([(0.3, 0, 0.1), (0.3, 0.2, 0), (0, 0.25, -0.4), (0.7, 0, 0), (np.pi / 4, 0.1, 0)]):
+        n = expm(1j * (a * np.kron(X, X) + b * np.kron(Y, Y) + c * np.kron(Z, Z)))
+        u = np.kron(u2(4 * k), u2(4 * k + 1)) @ n @ np.kron(u2(4 * k + 2), u2(4 * k + 3))
+        ph, ops = kak.decompose_two_qubit(u)
+        assert np.abs(ph * kak.ops_to_matrix(ops) - u).max() < 1e-10
+        assert sum(1 for o in ops if o[0] == "cx") == 2
 
 
 def test_random_two_qubit_gates():
