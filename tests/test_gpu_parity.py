@@ -376,7 +376,9 @@ def test_facade_readme_example(drv, capsys):
     assert abs(abs(np.vdot(dense, psi)) - abs(overlap)) < 1e-10
     # circ is the {cx, u3} circuit (qiskit_circuit.py:50); its source gate list has the reference's gate count
     assert circ.source.size() == sum(ref["gate_counts"][-1:])
-    assert circ.num_nonlocal_gates() == 3 * circ.source.num_nonlocal_gates()
+    # minimal CNOT counts: three per generic unitary, two where the completed isometry allows it (about half of them)
+    n2 = circ.source.num_nonlocal_gates()
+    assert 2 * n2 <= circ.num_nonlocal_gates() <= 3 * n2
     assert set(circ.count_ops()) == {"u3", "cx"} and circ.size() == sum(circ.count_ops().values())
     sv = circ.statevector().reshape(-1).cpu().numpy()  # axis i = qubit i, same as the oracle's dense vector
     assert abs(abs(np.vdot(dense, sv)) - abs(overlap)) < 1e-10
