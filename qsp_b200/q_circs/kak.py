@@ -26,6 +26,7 @@ _MAGIC = np.array([[1, 0, 0, 1j], [0, 1j, 1, 0], [0, 1j, -1, 0], [1, 0, 0, -1j]]
 _CX = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
 _XC = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128)
 _PERMS = [list(p) for p in itertools.permutations(range(4))]
+_PERMS_ARR = np.array(_PERMS)
 # diagonals of XX, YY, ZZ in the magic basis, and the all-ones column (global phase)
 _WEYL_BASIS = np.array([[1, -1, 1, 1], [1, 1, -1, 1], [-1, -1, -1, 1], [-1, 1, 1, 1]], dtype=np.float64)
 
@@ -166,59 +167,66 @@ def rx(t):
     return np.array([[c, -1j * s_], [-1j * s_, c]], dtype=np.complex128)
 
 
-def _locals_to_template(u, w, rng, tol=1e-9):
+def _locals_to_template(u, w, rng, tol=1e-9, uside=None):
     """(phase, a1, b1, a2, b2) with u = phase (a1 (x) b1) w (a2 (x) b2), or None when w is not locally equivalent
-    to u (the spectra of m^T m in the magic basis differ).  One gate; used for the 0/1/2-CNOT templates."""
-    us, phu = _su4(u[None])
+    to u (the spectra of m^T m in the magic basis differ).  One gate; used for the 1/2-CNOT templates.
+    uside = (up, lu, p, phu) of u when the caller has already diagonalised it."""
+    if uside is None:
+        us, phu = _su4(u[None])
+        up = _MAGIC.conj().T @ us @ _MAGIC
+        lu, p = _diag_symmetric_unitary(np.swapaxes(up, 1, 2) @ up, rng)
+        up, lu, p, phu = up[0], lu[0], p[0], phu[0]
+    else:
+        up, lu, p, phu = uside
     ws, phw = _su4(w[None])
-    up, wp = _MAGIC.conj().T @ us @ _MAGIC, _MAGIC.conj().T @ ws @ _MAGIC
-    lu, p = _diag_symmetric_unitary(np.swapaxes(up, 1, 2) @ up, rng)
+    wp = _MAGIC.conj().T @ ws @ _MAGIC
+    perms = _PERMS_ARR
     best = None
     for k in (0, 1):
         wk = wp * (1j ** k)
         lw, q = _diag_symmetric_unitary(np.swapaxes(wk, 1, 2) @ wk, rng)
-        for perm in _PERMS:
-            e = np.abs(lu[0] - lw[0][perm]).max()
-            if best is None or e < best[0]:
-                best = (e, k, perm, q[0], wk[0])
+        e = np.abs(lu[None, :] - lw[0][perms]).max(axis=1)
+        j = int(e.argmin())
+        if best is None or e[j] < best[0]:
+            best = (e[j], k, perms[j], q[0], wk[0])
+        if best[0] <= tol:
+            break
     e, k, perm, q, wk = best
     if e > tol:
         return None
-    q, p0 = q[:, perm], p[0].copy()
+    q, p0 = q[:, perm], p.copy()
     if np.linalg.det(q) * np.linalg.det(p0) < 0:
         p0[:, 0] *= -1
     o2 = q @ p0.T
-    o1 = up[0] @ o2.T @ wk.conj().T
-    l1, l2 = _MAGIC @ o1.real @ _MAGIC.conj().T, _MAGIC @ o2 @ _MAGIC.conj().T
-    a1, b1, p1, r1 = _kron_factor(l1[None])
-    a2, b2, p2, r2 = _kron_factor(l2[None])
-    return complex(phu[0] / phw[0] * (1j ** k) * p1[0] * p2[0]), a1[0], b1[0], a2[0], b2[0]
+    o1 = up @ o2.T @ wk.conj().T
+    l12 = np.stack([_MAGIC @ o1.real @ _MAGIC.conj().T, _MAGIC @ o2 @ _MAGIC.conj().T])
+    ab, bb, pp, _ = _kron_factor(l12)
+    return complex(phu / phw[0] * (1j ** k) * pp[0] * pp[1]), ab[0], bb[0], ab[1], bb[1]
 
 
-def _fewer_cnots(u, lam, rng):
+def _fewer_cnots(u, uside, rng):
     """Op list with one or two CNOTs when the unitary allows it (Shende-Bullock-Markov: two CNOTs suffice iff the
-    trace of m^T m is real, one iff its spectrum is {i, i, -i, -i}), else None.  lam: spectrum of m^T m."""
+    trace of m^T m is real, one iff its spectrum is {i, i, -i, -i}), else None.  uside: (up, spectrum of m^T m, p, phase)."""
+    lam = uside[1]
     for sgn in (1.0, -1.0):  # det^{1/4} leaves the overall sign of the spectrum open
         mu = sgn * lam
         if np.abs(np.sort_complex(np.round(mu, 9)) - np.sort_complex(np.round(np.conj(mu), 9))).max() > 1e-7:
             continue
         if np.abs(mu * mu + 1.0).max() < 1e-9 and abs(mu.sum()) < 1e-9:  # locally a CNOT
-            r = _locals_to_template(u, _CX, rng)
+            r = _locals_to_template(u, _CX, rng, uside=uside)
             if r is not None:
                 ph, a1, b1, a2, b2 = r
                 return ph, [("u", 0, a2), ("u", 1, b2), ("cx", 0, 1), ("u", 0, a1), ("u", 1, b1)]
         th = np.sort(np.abs(np.angle(mu)))  # {t2, t2, t1, t1}: 2(a+c) = t2, 2(a-c) = t1
         t2, t1 = 0.5 * (th[0] + th[1]), 0.5 * (th[2] + th[3])
         a, c = (t1 + t2) / 4, (t2 - t1) / 4
-        for aa, cc in ((a, c), (a, -c), (np.pi / 2 - a, c), (np.pi / 2 - a, -c)):
-            w = _CX @ np.kron(rx(2 * aa), rz(2 * cc)) @ _CX
-            r = _locals_to_template(u, w, rng)
-            if r is not None:
-                ph, a1, b1, a2, b2 = r
-                return ph, [("u", 0, a2), ("u", 1, b2), ("cx", 0, 1), ("u", 0, rx(2 * aa)), ("u", 1, rz(2 * cc)), ("cx", 0, 1),
-                            ("u", 0, a1), ("u", 1, b1)]
+        w = _CX @ np.kron(rx(2 * a), rz(2 * c)) @ _CX
+        r = _locals_to_template(u, w, rng, uside=uside)
+        if r is not None:
+            ph, a1, b1, a2, b2 = r
+            return ph, [("u", 0, a2), ("u", 1, b2), ("cx", 0, 1), ("u", 0, rx(2 * a)), ("u", 1, rz(2 * c)), ("cx", 0, 1),
+                        ("u", 0, a1), ("u", 1, b1)]
     return None
-
 
 def decompose_two_qubit_batch(u, rng=None):
     """u[n] (4x4 unitaries on kron(left, right)) -> dict of arrays:
@@ -244,7 +252,7 @@ def decompose_two_qubit_batch(u, rng=None):
     lu, p = _diag_symmetric_unitary(np.swapaxes(up, 1, 2) @ up, rng)
     # special unitaries (never the generic gates of the path): one or two CNOTs, handled one by one
     for i in np.nonzero(np.abs(lu.sum(axis=1).imag) < 1e-9)[0]:
-        r = _fewer_cnots(v[i], lu[i], rng)
+        r = _fewer_cnots(v[i], (up[i], lu[i], p[i], phu[i]), rng)
         if r is not None:
             out["special"][int(idx[i])] = r
             out["phase"][idx[i]] = r[0]
@@ -253,7 +261,7 @@ def decompose_two_qubit_batch(u, rng=None):
     ws, phw = _su4(w)
     wp = _MAGIC.conj().T @ ws @ _MAGIC
     # det^{1/4} is defined up to i^k: the spectra of up^T up and wp^T wp agree up to (-1)^k and a permutation
-    perms = np.array(_PERMS)
+    perms = _PERMS_ARR
     best_e = np.full(idx.size, np.inf)
     best_k = np.zeros(idx.size, dtype=int)
     best_q = np.zeros((idx.size, 4, 4))
