@@ -67,10 +67,10 @@ class MPSPreparation:
 
     def lcu_unitary_circuit(self, num_lcu_layers, verbose=False):
         """tsp.py:287-352: the target as a linear combination of num_lcu_layers D=2 circuits.  Returns
-        (overlap, circ); the tensor part runs on the device (qsp_b200.lcu), the ancilla-controlled LCU circuit
-        (q_circs.lcu_circuit_from_unitary_layers) is not emitted by this package: circ is None and
-        self.lcu_data carries kappas and unitaries for it."""
+        (overlap, circ); the tensor part runs on the device (qsp_b200.lcu), circ is the ancilla-controlled LCU
+        circuit (q_circs.lcu_circuit_from_unitary_layers: prep / mcx / cu3 / ccx gates, not transpiled further)."""
         from .lcu import lcu_unitary_circuit
+        from .q_circs import lcu_circuit_from_unitary_layers
 
         if self.phys_dim != 2:
             raise ValueError("only supports mps with physical dimesnion=2")
@@ -83,10 +83,14 @@ class MPSPreparation:
         # tsp.py:322-333 rebuilds sum_k kappa_k U_k|0..0> and takes norm_mps_ovrlap(encoded, target): the conjugate
         # of the last entry of data['overlaps'] (= norm_mps_ovrlap(target, encoded), evaluated on the device)
         overlap = np.conj(data["overlaps"][-1])
-        self.lcu_data["circ"] = None
-        print(f"overllap after lcu. preparation = {np.abs(overlap):.8f}, n_gates=n/a, n_2qg=n/a (LCU circuit emission "
-              "is outside this package)\n")
-        return overlap, None
+        circ, overlap_from_lcu_circ = lcu_circuit_from_unitary_layers(data["kappas"], data["unitaries"], self.L,
+                                                                      self.target_mps)
+        self.lcu_data["circ"] = circ
+        self.lcu_data["overlap_from_lcu_circ"] = overlap_from_lcu_circ
+        temp_str = "" if overlap_from_lcu_circ is None else f" (from circ {overlap_from_lcu_circ:0.8f})"
+        print(f"overllap after lcu. preparation = {np.abs(overlap):.8f}{temp_str}, "
+              f"n_gates={circ.size()}, n_2qg={circ.num_nonlocal_gates()}\n")
+        return overlap, circ
 
     def _encoded_overlap(self, unitaries):
         from .mps import gs_lst_to_gates

@@ -96,6 +96,24 @@ def test_lcu_edge_cases_on_the_emulator(name):
         assert abs(r["overlaps"][-1, 0]) > abs(r["overlaps"][0, 0])
 
 
+@pytest.mark.parametrize("L,chi,terms", [(6, 4, 4), (5, 3, 2), (6, 4, 1), (7, 4, 8)])
+def test_lcu_circuit_reproduces_the_encoded_state(L, chi, terms):
+    """qiskit_lcu_circuit.py:16-62 rebuilt (prep, mcx, controlled {cx,u3} synthesis of every unitary) and simulated:
+    the system state left when all ancillas read 0 is sum_k kappa_k U_k|0..0>."""
+    from qsp_b200.q_circs import lcu_circuit_from_unitary_layers
+
+    tg = _prepared(O.random_mps(L, chi, 3))
+    ref = O.lcu_unitary_circuit(tg, terms, completion="canonical", kappa_solver="closed")
+    layers = [[[[s, e, [np.asarray(g) for g in gs]] for s, e, gs in lay[0]]] for lay in ref["unitaries"]]
+    circ, ov = lcu_circuit_from_unitary_layers(ref["kappas"], layers, L, tg)
+    assert abs(ov - abs(ref["overlaps"][-1])) < 1e-12
+    k = int(np.log2(terms))
+    assert circ.num_qubits == L + k + 1 and circ.count_ops()["mcx"] == 2 * terms
+    enc = O.mps_to_dense(ref["encoded_mps"]).reshape(-1)
+    out = circ.system_state().reshape(-1)
+    assert abs(abs(np.vdot(enc, out)) / (np.linalg.norm(enc) * np.linalg.norm(out)) - 1) < 1e-12
+
+
 def test_mps_axpby_kernel_on_the_emulator():
     drv = HostDriver()
     xs, ys = [O.random_mps(5, 3, s) for s in range(2)], [O.random_mps(5, 2, 9 + s) for s in range(2)]
@@ -144,7 +162,10 @@ def test_lcu_facade(capsys):
     prep = MPSPreparation(arr, shape="lrp")
     overlap, circ = prep.lcu_unitary_circuit(num_lcu_layers=4)
     ref = O.lcu_unitary_circuit(O.prepare_target(arr, "lrp"), 4, completion="canonical", kappa_solver="closed")
-    assert abs(overlap - np.conj(ref["overlaps"][-1])) < 1e-10 and circ is None
+    assert abs(overlap - np.conj(ref["overlaps"][-1])) < 1e-10
+    # the ancilla-controlled LCU circuit, simulated: post-selected system state vs the target
+    assert abs(prep.lcu_data["overlap_from_lcu_circ"] - abs(overlap)) < 1e-10
+    assert circ.num_qubits == 10 + 2 + 1 and set(circ.count_ops()) == {"prep", "prep_dg", "mcx", "cu3", "ccx"}
     assert set(prep.lcu_data) >= {"kappas", "unitaries", "approx_mps_overlap", "it_Ds", "overlaps", "energies", "circ"}
     assert "preparing mps as linear combination of unitaries (num_lcu_layers=4)" in capsys.readouterr().out
     with pytest.raises(ValueError):
