@@ -89,6 +89,39 @@ class LcuCircuit:
         psi = self.statevector()
         return psi[(0,) * (self.k + 1)]
 
+    def transpile(self):
+        """The same circuit in {cx, u3} (tsp.py:340, `qiskit.transpile(circ, basis_gates=["cx", "u3"])`): state
+        preparation and every multi-controlled gate by the textbook constructions of controlled.py, one-qubit runs
+        merged.  Equal to this circuit on |0..0> up to the completion of the state-preparation unitaries, i.e. the
+        post-selected system state is the same.  Returns a CxU3Circuit."""
+        from . import controlled as C
+        from .circuit import CxU3Circuit
+
+        sink = C.GateSink()
+        x = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+        for name, qs, payload in self.gates:
+            if name == "prep":
+                C.state_preparation(sink, qs, payload)
+            elif name == "prep_dg":  # (prep of the payload)^dagger
+                tmp = C.GateSink()
+                C.state_preparation(tmp, qs, payload)
+                sink.gates.extend(C.invert(tmp.gates))
+                sink.phase -= tmp.phase
+            elif name == "mcx":
+                C.controlled_u_state(sink, qs[:-1], payload, qs[-1], x)
+            elif name == "cu3":
+                C.controlled_u(sink, [qs[0]], qs[1], kak.u3_matrix(*payload))
+            elif name == "ccx":
+                C.controlled_u(sink, [qs[0], qs[1]], qs[2], x)
+            else:
+                raise ValueError(name)
+        gates, ph = C.merge_one_qubit(sink.gates, self.num_qubits)
+        out = CxU3Circuit(self.num_qubits)
+        out.gates = gates
+        out.global_phase = sink.phase + ph
+        out.source = self
+        return out
+
 
 def lcu_circuit_from_unitary_layers(kappas, unitary_layers, L, target_mps=None):
     """qiskit_lcu_circuit.py:16-62.  unitary_layers[j] = [Gs_lst] of term j (as lcu_unitary_circuit returns them).

@@ -68,7 +68,7 @@ class MPSPreparation:
     def lcu_unitary_circuit(self, num_lcu_layers, verbose=False):
         """tsp.py:287-352: the target as a linear combination of num_lcu_layers D=2 circuits.  Returns
         (overlap, circ); the tensor part runs on the device (qsp_b200.lcu), circ is the ancilla-controlled LCU
-        circuit (q_circs.lcu_circuit_from_unitary_layers: prep / mcx / cu3 / ccx gates, not transpiled further)."""
+        circuit (q_circs.lcu_circuit_from_unitary_layers) in {cx, u3}."""
         from .lcu import lcu_unitary_circuit
         from .q_circs import lcu_circuit_from_unitary_layers
 
@@ -83,8 +83,9 @@ class MPSPreparation:
         # tsp.py:322-333 rebuilds sum_k kappa_k U_k|0..0> and takes norm_mps_ovrlap(encoded, target): the conjugate
         # of the last entry of data['overlaps'] (= norm_mps_ovrlap(target, encoded), evaluated on the device)
         overlap = np.conj(data["overlaps"][-1])
-        circ, overlap_from_lcu_circ = lcu_circuit_from_unitary_layers(data["kappas"], data["unitaries"], self.L,
+        high, overlap_from_lcu_circ = lcu_circuit_from_unitary_layers(data["kappas"], data["unitaries"], self.L,
                                                                       self.target_mps)
+        circ = high.transpile()  # tsp.py:340: {cx, u3}; circ.source keeps the prep / mcx / cu3 / ccx form
         self.lcu_data["circ"] = circ
         self.lcu_data["overlap_from_lcu_circ"] = overlap_from_lcu_circ
         temp_str = "" if overlap_from_lcu_circ is None else f" (from circ {overlap_from_lcu_circ:0.8f})"

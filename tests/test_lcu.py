@@ -114,6 +114,75 @@ def test_lcu_circuit_reproduces_the_encoded_state(L, chi, terms):
     assert abs(abs(np.vdot(enc, out)) / (np.linalg.norm(enc) * np.linalg.norm(out)) - 1) < 1e-12
 
 
+@pytest.mark.parametrize("L,chi,terms", [(5, 3, 2), (6, 4, 4), (5, 4, 8), (6, 4, 1)])
+def test_lcu_circuit_transpiled_to_cx_u3(L, chi, terms):
+    """tsp.py:340: the LCU circuit in {cx, u3} (state preparation, mcx with ctrl_state, cu3, ccx by the constructions
+    of q_circs/controlled.py) leaves the same system state -- same direction and same success amplitude -- when the
+    ancillas are post-selected on 0."""
+    from qsp_b200.q_circs import lcu_circuit_from_unitary_layers
+
+    tg = _prepared(O.random_mps(L, chi, 3))
+    ref = O.lcu_unitary_circuit(tg, terms, completion="canonical", kappa_solver="closed")
+    layers = [[[[s, e, [np.asarray(g) for g in gs]] for s, e, gs in lay[0]]] for lay in ref["unitaries"]]
+    high, _ = lcu_circuit_from_unitary_layers(ref["kappas"], layers, L, tg)
+    circ = high.transpile()
+    assert set(circ.count_ops()) == {"u3", "cx"} and circ.num_qubits == high.num_qubits
+    a = high.system_state().reshape(-1)
+    b = circ.statevector("cpu").numpy()[(0,) * (high.k + 1)].reshape(-1)
+    assert abs(abs(np.vdot(a, b)) / (np.linalg.norm(a) * np.linalg.norm(b)) - 1) < 1e-12
+    assert abs(np.linalg.norm(b) / np.linalg.norm(a) - 1) < 1e-10
+
+
+def test_multi_controlled_gates_and_state_preparation():
+    from scipy.stats import unitary_group
+
+    from qsp_b200.q_circs import controlled as C
+    from qsp_b200.q_circs import kak
+
+    def dense(gates, n):
+        u = np.eye(2 ** n, dtype=complex)
+        for name, q, par in gates:
+            m = np.zeros((2 ** n, 2 ** n), complex)
+            for j in range(2 ** n):
+                if name == "cx":
+                    m[j ^ (1 << q[1]) if (j >> q[0]) & 1 else j, j] = 1
+                else:
+                    g = kak.u3_matrix(*par)
+                    for b in (0, 1):
+                        m[(j & ~(1 << q[0])) | (b << q[0]), j] += g[b, (j >> q[0]) & 1]
+            u = m @ u
+        return u
+
+    for trial, nc in enumerate([0, 1, 1, 2, 2, 3, 3, 4]):
+        n = nc + 1
+        u = unitary_group.rvs(2, random_state=trial) if trial % 2 else np.array([[0, 1], [1, 0]], complex)
+        perm = [int(x) for x in np.random.default_rng(trial).permutation(n)]
+        controls, target = perm[:nc], perm[nc]
+        state = int(np.random.default_rng(trial + 5).integers(0, 2 ** nc)) if nc else 0
+        sink = C.GateSink()
+        C.controlled_u_state(sink, controls, state, target, u)
+        want = np.zeros((2 ** n, 2 ** n), complex)
+        for j in range(2 ** n):
+            fire = all(((j >> c) & 1) == ((state >> i) & 1) for i, c in enumerate(controls))
+            for b in (0, 1):
+                if fire:
+                    want[(j & ~(1 << target)) | (b << target), j] += u[b, (j >> target) & 1]
+                elif b == ((j >> target) & 1):
+                    want[j, j] = 1
+        assert np.abs(np.exp(1j * sink.phase) * dense(sink.gates, n) - want).max() < 1e-12
+    for k in (1, 2, 3, 4):
+        rng = np.random.default_rng(k)
+        v = rng.standard_normal(2 ** k) + 1j * rng.standard_normal(2 ** k)
+        v /= np.linalg.norm(v)
+        sink = C.GateSink()
+        C.state_preparation(sink, list(range(k)), v)
+        d = dense(sink.gates, k)
+        assert np.abs(np.exp(1j * sink.phase) * d[:, 0] - v).max() < 1e-12
+        assert np.abs(dense(C.invert(sink.gates), k) @ d - np.eye(2 ** k)).max() < 1e-12
+        merged, ph = C.merge_one_qubit(sink.gates, k)
+        assert np.abs(np.exp(1j * ph) * dense(merged, k) - d).max() < 1e-12 and len(merged) <= len(sink.gates)
+
+
 def test_mps_axpby_kernel_on_the_emulator():
     drv = HostDriver()
     xs, ys = [O.random_mps(5, 3, s) for s in range(2)], [O.random_mps(5, 2, 9 + s) for s in range(2)]
@@ -165,7 +234,8 @@ def test_lcu_facade(capsys):
     assert abs(overlap - np.conj(ref["overlaps"][-1])) < 1e-10
     # the ancilla-controlled LCU circuit, simulated: post-selected system state vs the target
     assert abs(prep.lcu_data["overlap_from_lcu_circ"] - abs(overlap)) < 1e-10
-    assert circ.num_qubits == 10 + 2 + 1 and set(circ.count_ops()) == {"prep", "prep_dg", "mcx", "cu3", "ccx"}
+    assert circ.num_qubits == 10 + 2 + 1 and set(circ.count_ops()) == {"u3", "cx"}
+    assert set(circ.source.count_ops()) == {"prep", "prep_dg", "mcx", "cu3", "ccx"}
     assert set(prep.lcu_data) >= {"kappas", "unitaries", "approx_mps_overlap", "it_Ds", "overlaps", "energies", "circ"}
     assert "preparing mps as linear combination of unitaries (num_lcu_layers=4)" in capsys.readouterr().out
     with pytest.raises(ValueError):
