@@ -2,6 +2,7 @@
 the cu3 / ccx / mcx / StatePreparation gates of the reference's LCU circuit (qiskit_lcu_circuit.py:30-38, tsp.py:340).
 
     C(U)      one control: e^{i g} u3(t, p, l) -> phase u1(g) on the control and the standard cu3 identity (two CNOTs)
+    CCX       the standard six-CNOT Toffoli
     C^n(U)    Barenco et al. 1995, lemma 7.5:  C(V)[c_n] . C^{n-1}X[-> c_n] . C(V^+)[c_n] . C^{n-1}X[-> c_n] . C^{n-1}V,  V^2 = U
     state preparation: one multi-controlled rotation per node of the amplitude tree (k <= 4 ancillas here)
 
@@ -65,6 +66,20 @@ def controlled_u(out, controls, target, u):
         _u3_exact(out, target, kak.u3_matrix(-th / 2, 0.0, -(ph + la) / 2))
         out.append(("cx", [c, target], ()))
         _u3_exact(out, target, kak.u3_matrix(th / 2, ph, 0.0))
+        return
+    if n == 2 and np.abs(u - _X).max() < 1e-13:
+        # the standard six-CNOT Toffoli (H, T, T^+ are exact u3 gates: no phase left over)
+        c1, c2 = controls
+        h = kak.u3_matrix(np.pi / 2, 0.0, np.pi)
+        t, tdg = _phase_gate(np.pi / 4), _phase_gate(-np.pi / 4)
+        for name, q, m in (("u", target, h), ("cx", (c2, target), None), ("u", target, tdg), ("cx", (c1, target), None),
+                           ("u", target, t), ("cx", (c2, target), None), ("u", target, tdg), ("cx", (c1, target), None),
+                           ("u", c2, t), ("u", target, t), ("u", target, h), ("cx", (c1, c2), None), ("u", c1, t),
+                           ("u", c2, tdg), ("cx", (c1, c2), None)):
+            if name == "u":
+                _u3_exact(out, q, m)
+            else:
+                out.append(("cx", [q[0], q[1]], ()))
         return
     v = _sqrt_unitary(u)
     last, rest = controls[-1], controls[:-1]
