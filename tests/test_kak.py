@@ -114,3 +114,17 @@ def test_identity_gates_are_dropped():
     gl.unitary(np.exp(0.3j) * np.eye(2), [2])
     circ = CxU3Circuit.from_gate_list(gl)
     assert circ.size() == 0 and abs(np.exp(1j * circ.global_phase) - np.exp(0.3j)) < 1e-12
+
+
+def test_class_boundaries_stay_exact():
+    """unitaries a hair away from the 0/1/2-CNOT classes: whichever template is chosen, the synthesis stays exact"""
+    from scipy.linalg import expm
+
+    X, Y, Z = np.array([[0, 1], [1, 0]], complex), np.array([[0, -1j], [1j, 0]]), np.diag([1.0, -1.0]).astype(complex)
+    u2 = lambda s: unitary_group.rvs(2, random_state=s)
+    for e in (1e-3, 1e-5, 1e-7, 3e-9, 1e-9, 3e-10, 1e-10, 1e-11, 1e-12, 1e-14):
+        for a, b, c in ((0.3, 0.2, e), (np.pi / 4, e, 0), (e, 0, 0), (np.pi / 4 + e, 0, 0), (0.3, e, e)):
+            n = expm(1j * (a * np.kron(X, X) + b * np.kron(Y, Y) + c * np.kron(Z, Z)))
+            u = np.kron(u2(1), u2(2)) @ n @ np.kron(u2(3), u2(4))
+            ph, ops = kak.decompose_two_qubit(u)
+            assert np.abs(ph * kak.ops_to_matrix(ops) - u).max() < 2e-10, (e, a, b, c)
