@@ -364,6 +364,12 @@ def main():
         dist.destroy_process_group()
 
 
+def _runtime_dev_lib():
+    from qsp_b200 import _runtime
+
+    return _runtime.dev_lib()  # probes live in libqsp_b200_dev.so (include/qsp_b200_dev.h), not in the product library
+
+
 def fp64_peak(torch, lib, dev, sms, tensor=False):
     """FP64 throughput measured in-run (TFLOP/s): MEASURED_PEAKS.json has no FP64 entry.
     tensor=False: DFMA (the pipe the kernels use); tensor=True: warp-level DMMA (mma.sync m8n8k4.f64)."""
@@ -372,6 +378,7 @@ def fp64_peak(torch, lib, dev, sms, tensor=False):
     out = torch.zeros(8, dtype=torch.float64, device=dev)
     s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     blocks, threads, iters = sms * 8, 256, 20000
+    lib = _runtime_dev_lib()
     probe = lib.qsp_dmma_probe if tensor else lib.qsp_dfma_probe
     flops = blocks * (threads // 32) * iters * 8 * 512.0 if tensor else blocks * threads * iters * 32.0
     best = 0.0

@@ -11,7 +11,9 @@
  *    host); nothing is allocated behind the caller's back: scratch comes from `work`,
  *    sized by the matching *_workspace_bytes() query;
  *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per
- *    stream, one device per call;
+ *    stream and per host thread (the library keeps no mutable process-wide state besides an atomic
+ *    launch tally; the last-error string and the optional profile buffer are per host thread), one
+ *    device per call;
  *  - complex128 = two doubles (re, im);
  *  - a batch of B independent MPS of L sites is stored as mps[B][L][D][2][D]: element
  *    (l, p, r) of a site at (l*2+p)*D + r, D = padded bond; the live extent of bond j of
@@ -159,26 +161,10 @@ int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bonds, int B, 
                     qsp_c128* dis_overlaps, qsp_c128* G, int32_t* kind, double* d2_svals, qsp_c128* final_mps,
                     int32_t* final_bonds, int32_t* status, void* work, size_t work_bytes, void* stream);
 
-/* Measurement aid: when set (device pointer to >= 8*grid int64, zeroed by the caller), every
- * qsp_right_compress launch adds per-CTA clock64 cycles: [0] A*C GEMM, [1] staging, [2] Jacobi,
+/* Measurement aid (state of the calling host thread): when set (device pointer to >= 8*grid int64, zeroed by the
+ * caller), every qsp_right_compress launch issued by this thread adds per-CTA clock64 cycles: [0] A*C GEMM, [1] staging, [2] Jacobi,
  * [3] ranking, [4] Vh/U s, [5] Jacobi sweeps, [6] sites.  NULL (default) disables it. */
 void qsp_set_profile_buffer(void* buf);
-
-/* Development aid: Jacobi micro-benchmark, W[B][nrows][ldw] orthogonalised in place (ldw a
- * multiple of 32), nt threads per CTA. */
-int qsp_jacobi_bench_fat(qsp_c128* W, int nrows, int ldw, int B, int* sweeps, int* ok, void* stream);
-int qsp_smem_probe(double* out, int blocks, int iters, int mode, void* stream); /* shared-memory bandwidth probe */
-void qsp_jacobi_variant(int bits); /* timing experiments: disables parts of the Jacobi round (results invalid) */
-void qsp_debug_flags(int flags);    /* test hook: bit 0 = take the large-bond left-canonise path at any size */
-int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int nt, int* sweeps, int* ok, void* stream);
-
-/* Measurement aid: blocks x threads threads each run `iters` rounds of 16 independent
- * double-precision FMAs (flops = blocks*threads*iters*32).  bench.py times it to obtain the
- * FP64 roofline denominator, which MEASURED_PEAKS.json does not carry. */
-int qsp_dfma_probe(double* out, int blocks, int threads, int iters, void* stream);
-/* Same for the FP64 tensor pipe: `iters` rounds of 8 independent warp-level DMMA (mma.sync m8n8k4.f64),
- * flops = blocks*(threads/32)*iters*8*512. */
-int qsp_dmma_probe(double* out, int blocks, int threads, int iters, void* stream);
 
 #ifdef __cplusplus
 }

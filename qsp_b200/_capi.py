@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.environ.get("QSP_B200_LIB") or os.path.join(_HERE, "libqsp_b200.so")
 
 ST_JACOBI_NOCONV, ST_BOND_OVERFLOW, ST_NONUNITARY, ST_DEGENERATE, ST_BADNORM = 1, 2, 4, 8, 16
+ST_FATAL = ST_JACOBI_NOCONV | ST_BOND_OVERFLOW | ST_NONUNITARY | ST_BADNORM  # ST_DEGENERATE is a report, not a failure
 FLAG_SECOND_PASS, FLAG_NO_ENCODED = 1, 2
 ERRORS = {1: "QSP_ERR_ARG", 2: "QSP_ERR_UNSUPPORTED", 3: "QSP_ERR_WORKSPACE", 4: "QSP_ERR_CUDA"}
 
@@ -23,7 +24,6 @@ _SIGNATURES = {
     "qsp_launch_count": (C.c_longlong, []),
     "qsp_left_canonize_workspace_bytes": (_sz, [_i, _i, _i]),
     "qsp_left_canonize": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, _p]),
-    "qsp_debug_flags": (None, [_i]),
     "qsp_right_compress_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "qsp_right_compress": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _d, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "qsp_generate_unitaries": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
@@ -41,16 +41,23 @@ _SIGNATURES = {
     "qsp_encoded_overlap": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _d, _p, _p, _p, _sz, _p]),
     "qsp_seq_prepare_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "qsp_set_profile_buffer": (None, [_p]),
+    "qsp_seq_prepare": (_i, [_p, _p, _i, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+}
+
+# libqsp_b200_dev.so only (include/qsp_b200_dev.h): development hooks, probes, micro-benchmarks
+_DEV_SIGNATURES = {
+    "qsp_debug_flags": (None, [_i]),
     "qsp_jacobi_bench_fat": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "qsp_smem_probe": (_i, [_p, _i, _i, _i, _p]),
     "qsp_jacobi_variant": (None, [_i]),
     "qsp_jacobi_bench": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "qsp_dfma_probe": (_i, [_p, _i, _i, _i, _p]),
     "qsp_dmma_probe": (_i, [_p, _i, _i, _i, _p]),
-    "qsp_seq_prepare": (_i, [_p, _p, _i, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
+DEV_EXPORTS = tuple(_DEV_SIGNATURES)
+DEV_LIB = os.path.join(_HERE, "libqsp_b200_dev.so")
 
 
 class QspError(RuntimeError):
@@ -60,7 +67,7 @@ class QspError(RuntimeError):
 class QspLib:
     """Thin, checked view of the shared library."""
 
-    def __init__(self, path=DEFAULT_LIB):
+    def __init__(self, path=DEFAULT_LIB, dev=False):
         if not os.path.exists(path):
             raise QspError(
                 f"{path} not found: the CUDA library is not built. Run `python -c 'import __graft_entry__ as g; "
@@ -68,7 +75,8 @@ class QspLib:
             )
         self.path = path
         self.dll = C.CDLL(path)
-        for name, (res, args) in _SIGNATURES.items():
+        self._sigs = dict(_SIGNATURES, **_DEV_SIGNATURES) if dev else _SIGNATURES
+        for name, (res, args) in self._sigs.items():
             fn = getattr(self.dll, name)
             fn.restype, fn.argtypes = res, args
             setattr(self, "_" + name, fn)
@@ -88,7 +96,7 @@ class QspLib:
         # qsp_xxx(...) -> checked call for int-returning entry points, raw for the queries
         if name.startswith("qsp_"):
             fn = object.__getattribute__(self, "_" + name)
-            if _SIGNATURES[name][0] is _i and not name.endswith(("version", "build")):
+            if self._sigs[name][0] is _i and not name.endswith(("version", "build")):
 
                 def call(*a):
                     self.check(fn(*a), name)

@@ -5,7 +5,7 @@ import ctypes
 import os
 import subprocess
 
-from ._capi import DEFAULT_LIB, QspError, QspLib
+from ._capi import DEFAULT_LIB, DEV_LIB, QspError, QspLib
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
@@ -19,12 +19,13 @@ def build(verbose=False, force=False):
     """nvcc build of qsp_b200/csrc -> qsp_b200/libqsp_b200.so (sm_100a; cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "qsp_b200.h"))
-    if not force and os.path.exists(DEFAULT_LIB):
-        if os.path.getmtime(DEFAULT_LIB) >= max(os.path.getmtime(s) for s in srcs):
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "qsp_b200_dev.h"))
+    if not force and os.path.exists(DEFAULT_LIB) and os.path.exists(DEV_LIB):
+        if min(os.path.getmtime(DEFAULT_LIB), os.path.getmtime(DEV_LIB)) >= max(os.path.getmtime(s) for s in srcs):
             return DEFAULT_LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        os.path.join(CSRC, "qsp_capi.cu"), "-o", DEFAULT_LIB]
-    subprocess.check_call(cmd)
+    for src, out in (("qsp_capi.cu", DEFAULT_LIB), ("qsp_dev.cu", DEV_LIB)):
+        cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, src), "-o", out]
+        subprocess.check_call(cmd)
     return DEFAULT_LIB
 
 
@@ -46,6 +47,21 @@ def lib():
             raise QspError(f"{DEFAULT_LIB} is not a device build")
         _lib = l
     return _lib
+
+
+_dev_lib = None
+
+
+def dev_lib():
+    """libqsp_b200_dev.so (include/qsp_b200_dev.h): probes and micro-benchmarks for bench.py / scripts/."""
+    global _dev_lib
+    if _dev_lib is None:
+        lib()  # same preconditions as the product library
+        l = QspLib(DEV_LIB, dev=True)
+        if not l.is_device_build():
+            raise QspError(f"{DEV_LIB} is not a device build")
+        _dev_lib = l
+    return _dev_lib
 
 
 def current_stream_ptr():

@@ -121,3 +121,5 @@ __device__ __forceinline__ double block_max(double v, double* red) {
 #define QSP_ST_NONUNITARY 4      // a generated gate failed the unitarity check
 #define QSP_ST_DEGENERATE 8      // D=2 Schmidt pair degenerate: completion gauge ill-defined
 #define QSP_ST_BADNORM 16        // zero / non-finite norm
+// relative gap (s_a - s_b) / s_0 below which two Schmidt values at the D=2 cut count as degenerate
+#define QSP_DEGENERATE_GAP 1e-6

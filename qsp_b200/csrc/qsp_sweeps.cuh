@@ -634,9 +634,13 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
 
   // dynamic instance queue: Jacobi sweep counts differ per instance, so CTAs pull work instead of striding
   int* s_inst = (int*)(red + 56);
+  int* s_bad = (int*)(red + 57);  // a thread saw a non-finite singular value
   for (;;) {
     __syncthreads();
-    if (tid == 0) *s_inst = atomicAdd(P.queue, 1);
+    if (tid == 0) {
+      *s_inst = atomicAdd(P.queue, 1);
+      *s_bad = 0;
+    }
     __syncthreads();
     const int inst = *s_inst;
     if (inst >= P.B) break;
@@ -845,6 +849,13 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         }
       }
       __syncthreads();
+      // non-finite input: rank it last (a NaN would break the total order below and leave perm[] slots unwritten)
+      for (int r = tid; r < nrows; r += nt)
+        if (!(norms[r] <= 1e300)) {
+          norms[r] = 0.0;
+          *s_bad = 1;
+        }
+      __syncthreads();
       for (int r = tid; r < nrows; r += nt) {
         const double s = norms[r];
         int rank = 0;
@@ -864,6 +875,13 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         k = kmax;
       }
       k = imax(k, 1);
+      if (P.max_bond == 2 && k == 2) {
+        // D=2 truncation (core.py:16-18): a degenerate kept pair, or a cut through a degenerate pair, leaves the D=2
+        // state / its bond gauge -- and with it the completed unitaries -- ill-defined: report it
+        const double s0 = smax, s1 = norms[perm[1]], s2 = nrows > 2 ? norms[perm[2]] : -1.0;
+        if (s0 - s1 < QSP_DEGENERATE_GAP * s0 || (s2 >= 0.0 && s1 - s2 < QSP_DEGENERATE_GAP * s0 && s2 > P.cutoff * s0))
+          st |= QSP_ST_DEGENERATE;
+      }
       if (P.svals) {
         double* sv = P.svals + ((long)inst * (L - 1) + (i - 1)) * P.nsv;
         for (int q = tid; q < P.nsv; q += nt) sv[q] = (q < nrows) ? norms[perm[q]] : 0.0;
@@ -913,6 +931,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       rp = k;
       __syncthreads();
     }
+    if (*s_bad) st |= QSP_ST_BADNORM;
     if (tid == 0 && P.status && st) P.status[inst] |= st;
     __syncthreads();
   }

@@ -150,6 +150,16 @@ class Engine:
         self.lib.qsp_generate_unitaries(_p(d2), _p(d2b), B, L, _p(G), _p(kind), _p(status), _runtime.current_stream_ptr())
         return G, kind, status
 
+    def apply_layer(self, mps, bonds, G, kind, Dout, inverse):
+        """gate part of apply_(inverse_)unitary_layer_on_wfn (core.py:126-138, 224-240): exact, bonds double inside a
+        segment.  inverse: mps must be left canonical (I2); forward: right canonical (I4)."""
+        B, L, Din = mps.shape[0], mps.shape[1], mps.shape[2]
+        out, bo, status = self.empty_c(B, L, Dout, 2, Dout), self.zeros_i(B, L + 1), self.zeros_i(B)
+        fn = self.lib.qsp_apply_inverse_layer if inverse else self.lib.qsp_apply_forward_layer
+        fn(_p(mps), _p(bonds), Din, _p(G.contiguous()), _p(kind.contiguous()), _p(out), _p(bo), Dout, B, L, _p(status),
+           _runtime.current_stream_ptr())
+        return out, bo, status
+
     def overlap(self, a, ba, b, bb):
         """sum_x a(x) conj(b(x)) per instance (numerator of norm_mps_ovrlap(a, b), helper_routines.py:69)"""
         B, L, Da, Db = a.shape[0], a.shape[1], a.shape[2], b.shape[2]

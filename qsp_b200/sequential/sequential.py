@@ -2,20 +2,14 @@
 qsp/sequential/core.py (generate_bond_d_unitary :12-22, apply_unitary_layers_on_wfn
 :217-221, apply_inverse_unitary_layer_on_wfn :224-240).  Same names, arguments and
 returned structures; every tensor operation is a call into libqsp_b200.so."""
-import ctypes
-
 import numpy as np
 import torch
 
-from .. import _runtime
-from ..engine import CUTOFF, Engine, pack_mps_list, unpack_mps, working_bond
+from .._capi import ST_DEGENERATE, ST_FATAL
+from ..engine import Engine, pack_mps_list, unpack_mps, working_bond
 from ..mps import MPSState, gates_to_gs_lst, gs_lst_to_gates
 from ..q_circs import circuit_from_unitary_layers
 from ..tsp_helper_routines.helper_routines import unitaries_sanity_check, unitaries_specs
-
-
-def _p(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
 def _to_dev(eng, arrays, D):
@@ -24,7 +18,7 @@ def _to_dev(eng, arrays, D):
 
 
 def _raise_on_status(status, what):
-    st = int(status.max().item()) if status.numel() else 0
+    st = (int(torch.bitwise_or(status, 0).max().item()) if status.numel() else 0) & ST_FATAL
     if st:
         raise RuntimeError(f"{what}: device status bits {st:#x} (see QSP_ST_* in include/qsp_b200.h)")
 
@@ -53,7 +47,7 @@ def sequential_unitary_circuit(mps, italic_D, do_compression=False, max_bond_dim
     status = int(res.status[0].item())
     if status & 4:
         raise AssertionError("every G in the list should be an unitary")
-    if status:
+    if status & ST_FATAL:
         raise RuntimeError(f"sequential_unitary_circuit: device status bits {status:#x}")
     G = res.G[:, 0].cpu().numpy()
     kind = res.kind[:, 0].cpu().numpy()
@@ -90,29 +84,20 @@ def sequential_unitary_circuit(mps, italic_D, do_compression=False, max_bond_dim
         "overlap_from_seq_circ": overlap_from_seq_circ,
         # extras (not in the reference dict): per-bond singular values of each D=2 truncation
         "d2_singular_values": res.d2_svals[:, 0].cpu().numpy(),
+        # QSP_ST_DEGENERATE: a D=2 cut went through a degenerate Schmidt pair (the unitaries are then one valid
+        # choice among several)
+        "degenerate_d2_cut": bool(status & ST_DEGENERATE),
     }
 
 
 def generate_bond_d_unitary(psi, engine=None):
     """core.py:12-22: D=2 truncation of psi and the unitary layer that prepares it."""
     eng = engine or Engine()
-    L = psi.L
-    D = psi.max_bond()
-    a, b = _to_dev(eng, psi.arrays, D)
-    B = 1
-    st = torch.zeros(B, dtype=torch.int32, device=eng.device)
-    s = _runtime.current_stream_ptr()
-    eng.lib.qsp_left_canonize(_p(a), _p(b), B, L, D, _p(st), s)
-    d2 = torch.empty((B, L, 2, 2, 2), dtype=torch.complex128, device=eng.device)
-    d2b = torch.empty((B, L + 1), dtype=torch.int32, device=eng.device)
-    nb = eng.lib.qsp_right_compress_workspace_bytes(B, L, D, 2)
-    work = torch.empty(nb, dtype=torch.uint8, device=eng.device)
-    eng.lib.qsp_right_compress(_p(a), _p(b), D, _p(d2), _p(d2b), 2, B, L, 2, CUTOFF, 1, None, 0, None, _p(st),
-                               _p(work), nb, s)
-    G = torch.empty((B, L, 4, 4), dtype=torch.complex128, device=eng.device)
-    kind = torch.empty((B, L), dtype=torch.int32, device=eng.device)
-    eng.lib.qsp_generate_unitaries(_p(d2), _p(d2b), B, L, _p(G), _p(kind), _p(st), s)
-    _raise_on_status(st, "generate_bond_d_unitary")
+    a, b = _to_dev(eng, psi.arrays, psi.max_bond())
+    st = eng.left_canonize(a, b)
+    d2, d2b, st2, _, _ = eng.right_compress(a, b, 2, max_bond=2, normalize=1)
+    G, kind, st3 = eng.generate_unitaries(d2, d2b)
+    _raise_on_status(st | st2 | st3, "generate_bond_d_unitary")
     return gates_to_gs_lst(G[0].cpu().numpy(), kind[0].cpu().numpy())
 
 
@@ -123,33 +108,20 @@ def _apply_layer(eng, arrays, Gs_lst, inverse, compress):
     G, kind = gs_lst_to_gates(Gs_lst, L)
     G = torch.from_numpy(G[None]).to(eng.device)
     kind = torch.from_numpy(kind[None]).to(eng.device)
-    st = torch.zeros(1, dtype=torch.int32, device=eng.device)
-    s = _runtime.current_stream_ptr()
-    out = torch.empty((1, L, 2 * D, 2, 2 * D), dtype=torch.complex128, device=eng.device)
-    ob = torch.empty((1, L + 1), dtype=torch.int32, device=eng.device)
+    st = eng.left_canonize(a, b)
     if inverse:
         # the exact product needs a left-canonical input
-        eng.lib.qsp_left_canonize(_p(a), _p(b), 1, L, D, _p(st), s)
-        eng.lib.qsp_apply_inverse_layer(_p(a), _p(b), D, _p(G), _p(kind), _p(out), _p(ob), 2 * D, 1, L, _p(st), s)
+        out, ob, st2 = eng.apply_layer(a, b, G, kind, 2 * D, inverse=True)
     else:
-        # ... and the forward product a right-canonical one
-        tmp = torch.empty_like(a)
-        tb = torch.empty_like(b)
-        nb = eng.lib.qsp_right_compress_workspace_bytes(1, L, D, D)
-        work = torch.empty(nb, dtype=torch.uint8, device=eng.device)
-        eng.lib.qsp_left_canonize(_p(a), _p(b), 1, L, D, _p(st), s)
-        eng.lib.qsp_right_compress(_p(a), _p(b), D, _p(tmp), _p(tb), D, 1, L, 0, CUTOFF, 0, None, 0, None, _p(st),
-                                   _p(work), nb, s)
-        eng.lib.qsp_apply_forward_layer(_p(tmp), _p(tb), D, _p(G), _p(kind), _p(out), _p(ob), 2 * D, 1, L, _p(st), s)
-    if compress:
-        res = torch.empty_like(out)
-        rb = torch.empty_like(ob)
-        nb = eng.lib.qsp_right_compress_workspace_bytes(1, L, 2 * D, 2 * D)
-        work = torch.empty(nb, dtype=torch.uint8, device=eng.device)
-        eng.lib.qsp_left_canonize(_p(out), _p(ob), 1, L, 2 * D, _p(st), s)
-        eng.lib.qsp_right_compress(_p(out), _p(ob), 2 * D, _p(res), _p(rb), 2 * D, 1, L, 0, CUTOFF, 0, None, 0, None,
-                                   _p(st), _p(work), nb, s)
-        out, ob = res, rb
+        # ... and the forward product a right-canonical one (I4)
+        tmp, tb, st2, _, _ = eng.right_compress(a, b, D)
+        out, ob, st3 = eng.apply_layer(tmp, tb, G, kind, 2 * D, inverse=False)
+        st2 = st2 | st3
+    st = st | st2
+    if compress:  # compress('right'), core.py:140
+        st = st | eng.left_canonize(out, ob)
+        out, ob, st2, _, _ = eng.right_compress(out, ob, 2 * D)
+        st = st | st2
     _raise_on_status(st, "apply layer")
     return unpack_mps(out, ob)[0]
 

@@ -5,6 +5,7 @@ examples/benchmarks.py:49-61)."""
 import numpy as np
 import torch
 
+from ._capi import ST_FATAL
 from .engine import Engine, pack_mps_list, unpack_mps, working_bond
 from .mps import MPSState, gates_to_gs_lst, to_lpr
 from .sequential import sequential_unitary_circuit
@@ -33,7 +34,7 @@ class MPSPreparation:
         a, b = torch.from_numpy(a).to(self._engine.device), torch.from_numpy(b).to(self._engine.device)
         # normalize(); normalize(); compress('right')  (tsp.py:68-72)
         st = self._engine.prepare_target(a, b)
-        if int(st.max().item()):
+        if int(st.max().item()) & ST_FATAL:
             raise RuntimeError(f"target preparation failed with device status {int(st.max().item()):#x}")
         target_mps = MPSState(unpack_mps(a, b)[0])
         target_mps._prepared = True
@@ -121,6 +122,7 @@ class BatchedMPSPreparation:
             self.mps = torch.from_numpy(a).to(self.engine.device)
             self.bonds = torch.from_numpy(b).to(self.engine.device)
         self.B, self.L = self.mps.shape[0], self.mps.shape[1]
+        self.status = torch.zeros(self.B, dtype=torch.int32, device=self.engine.device)
         if not prepared:
             self.status = self.engine.prepare_target(self.mps, self.bonds)
         self.seq_data = None
@@ -141,9 +143,10 @@ class BatchedMPSPreparation:
             tgt[:, :, :m, :, :m] = self.mps[:, :, :m, :, :m]
         res = self.engine.seq_prepare(tgt, self.bonds, num_seq_layers, max_bond=mb, overlaps_gap=overlaps_gap,
                                       second_pass=second_pass, chunk=chunk)
+        res.status |= self.status  # a target flagged during preparation stays flagged
         self.seq_data = res
         if check:
-            bad = torch.nonzero(res.status).flatten()
+            bad = torch.nonzero(res.status & ST_FATAL).flatten()
             if bad.numel():
                 raise RuntimeError(f"{bad.numel()} of {self.B} instances failed, first: instance {int(bad[0])} "
                                    f"status {int(res.status[bad[0]]):#x} (QSP_ST_* in include/qsp_b200.h)")
@@ -156,9 +159,10 @@ class BatchedMPSPreparation:
 
         r = lcu_unitary_circuit_batched(self.engine, self.mps, self.bonds, num_lcu_layers, do_compression, max_bond_dim,
                                         overlaps_gap)
+        r["status"] = r["status"] | self.status.cpu().numpy()
         self.lcu_data = r
-        if check and r["status"].any():
-            bad = np.nonzero(r["status"])[0]
+        if check and (r["status"] & ST_FATAL).any():
+            bad = np.nonzero(r["status"] & ST_FATAL)[0]
             raise RuntimeError(f"{bad.size} of {self.B} instances failed, first: instance {int(bad[0])} "
                                f"status {int(r['status'][bad[0]]):#x} (QSP_ST_* in include/qsp_b200.h)")
         return r["overlaps"][-1], r

@@ -41,19 +41,6 @@ def norm_mps_ovrlap(mps1, mps2, engine=None):
     D = max(mps1.max_bond(), mps2.max_bond())
     a, ba = pack_mps_list([mps1.arrays], D)
     b, bb = pack_mps_list([mps2.arrays], D)
-    dev = eng.device
-    a, ba, b, bb = (torch.from_numpy(x).to(dev) for x in (a, ba, b, bb))
-    import ctypes
-
-    from .. import _runtime
-
-    nb = eng.lib.qsp_overlap_workspace_bytes(1, mps1.L, D, D)
-    work = torch.empty(nb, dtype=torch.uint8, device=dev)
-    res = torch.empty(3, dtype=torch.complex128, device=dev)
-    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
-    s = _runtime.current_stream_ptr()
-    for k, (x, bx, y, by) in enumerate(((a, ba, b, bb), (a, ba, a, ba), (b, bb, b, bb))):
-        eng.lib.qsp_overlap(p(x), p(bx), D, p(y), p(by), D, 1, mps1.L, ctypes.c_void_p(res[k:].data_ptr()), p(work),
-                            nb, s)
-    r = res.cpu().numpy()
+    a, ba, b, bb = (torch.from_numpy(x).to(eng.device) for x in (a, ba, b, bb))
+    r = [complex(eng.overlap(x, bx, y, by)[0].item()) for x, bx, y, by in ((a, ba, b, bb), (a, ba, a, ba), (b, bb, b, bb))]
     return r[0] / np.sqrt(r[1] * r[2])

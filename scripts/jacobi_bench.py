@@ -6,7 +6,7 @@ from qsp_b200 import _runtime
 nrows, ldw, nt = (int(x) for x in sys.argv[1:4])
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 148
 var = int(os.environ.get("JVAR", "0"))
-lib = _runtime.lib(); dev = torch.device("cuda:0")
+lib = _runtime.dev_lib(); dev = torch.device("cuda:0")
 lib.qsp_jacobi_variant(var)
 g = torch.Generator(device=dev); g.manual_seed(0)
 W0 = torch.complex(torch.randn((B, nrows, ldw), generator=g, device=dev, dtype=torch.float64),

@@ -10,7 +10,9 @@ reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 enc = os.environ.get("PROBE_ENC", "1") == "1"
 dev = torch.device("cuda:0")
 eng = Engine()
-if os.environ.get('QSP_DEBUG_FLAGS'):
+if os.environ.get('QSP_DEBUG_FLAGS'):  # the hooks live in libqsp_b200_dev.so: run the whole path through it
+    from qsp_b200 import _runtime
+    eng.lib = _runtime.dev_lib()
     eng.lib.qsp_debug_flags(int(os.environ['QSP_DEBUG_FLAGS'], 0))
 raw, b0 = synth_batch(torch, B, L, chi, dev, 1)
 t0 = time.time(); st = eng.prepare_target(raw, b0); torch.cuda.synchronize()

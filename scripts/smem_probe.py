@@ -2,7 +2,7 @@ import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from qsp_b200 import _runtime
-lib = _runtime.lib(); dev = torch.device("cuda:0")
+lib = _runtime.dev_lib(); dev = torch.device("cuda:0")
 out = torch.zeros(8, dtype=torch.float64, device=dev)
 s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 iters = 20000

@@ -23,13 +23,13 @@ CSRC = os.path.join(ROOT, "qsp_b200", "csrc")
 def build_emu(force=False):
     """g++ -DQSP_EMU build of qsp_b200/csrc (fibers instead of CUDA threads). Tests only."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(EMU_DIR, "cuda_emu.h")]
-    srcs.append(os.path.join(ROOT, "include", "qsp_b200.h"))
+    srcs += [os.path.join(ROOT, "include", "qsp_b200.h"), os.path.join(ROOT, "include", "qsp_b200_dev.h")]
     if not force and os.path.exists(EMU_LIB):
         if os.path.getmtime(EMU_LIB) >= max(os.path.getmtime(s) for s in srcs):
             return EMU_LIB
     os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
     cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DQSP_EMU", "-x", "c++",
-           os.path.join(CSRC, "qsp_capi.cu"), "-I", EMU_DIR, "-I", CSRC, "-o", EMU_LIB]
+           os.path.join(CSRC, "qsp_dev.cu"), "-I", EMU_DIR, "-I", CSRC, "-o", EMU_LIB]
     subprocess.check_call(cmd)
     return EMU_LIB
 
@@ -120,7 +120,7 @@ class HostDriver:
     """Unit-level calls on numpy buffers (emulated build)."""
 
     def __init__(self, lib=None):
-        self.lib = lib or QspLib(build_emu())
+        self.lib = lib or QspLib(build_emu(), dev=True)
 
     @staticmethod
     def p(x):

@@ -10,8 +10,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "qsp_b200.h")).read()
+def declared_symbols(header="qsp_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(qsp_[a-z0-9_]+)\s*\(", src)))
 
@@ -30,6 +30,16 @@ def test_device_library_builds_and_exports_header_symbols():
     assert sorted(EXPORTS) == syms  # the python binding covers the whole header
     dll.qsp_is_device_build.restype = ctypes.c_int
     assert dll.qsp_is_device_build() == 1
+    # development aids stay out of the product library and its header
+    from qsp_b200._capi import DEV_EXPORTS, DEV_LIB
+
+    dev_syms = declared_symbols("qsp_b200_dev.h")
+    assert sorted(DEV_EXPORTS) == dev_syms and not set(dev_syms) & set(syms)
+    dev = ctypes.CDLL(DEV_LIB)
+    for s in dev_syms:
+        assert hasattr(dev, s) and not hasattr(dll, s), s
+    for s in syms:
+        assert hasattr(dev, s), s
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not available")
@@ -60,7 +70,7 @@ def test_emulated_build_identifies_itself():
     from helpers import build_emu
     from qsp_b200._capi import QspLib
 
-    lib = QspLib(build_emu())
+    lib = QspLib(build_emu(), dev=True)
     assert not lib.is_device_build()
 
 

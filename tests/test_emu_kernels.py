@@ -306,7 +306,8 @@ def test_edge_cases(drv, name):
     t = _prepared(raw)
     a, b = pack_batch([t], D)
     r = drv.seq_prepare(a, b, layers, max_bond=mb)
-    assert r["status"][0] == 0
+    # the GHZ state's Schmidt pair (1/sqrt2, 1/sqrt2) is exactly degenerate: reported, not an error
+    assert r["status"][0] == (8 if name == "ghz_degenerate_schmidt" else 0)
     dev_layers = [gates_to_layers(r["G"][j, 0], r["kind"][j, 0]) for j in range(layers)]
     kw = dict(do_compression=mb > 0, max_bond_dim=mb or None)
     tf = O.sequential_unitary_circuit(t, layers, unitaries_override=dev_layers, **kw)
