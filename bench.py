@@ -3,12 +3,15 @@
 MPS/sec at L=100, chi=64, 4 layers, do_compression=True, max_bond_dim=chi).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                  [--L 100 --chi 64 --layers 4 --batch 296]
+                  [--L 100 --chi 64 --layers 4] [--batch-total 4096 | --batch PER_GPU]
 
-A step = one pass of the hot path (the whole layer loop incl. the encoded-state overlaps)
-over one batch of `batch` synthetic random MPS per GPU.  Prints ONE JSON line (rank 0).
-Under torchrun every rank owns its own instances (weak scaling, no data-path collective
-except the final all-gather of overlaps + unitaries the path's callers need).
+A step = one pass of the hot path (the whole layer loop incl. the encoded-state overlaps) over one
+batch of synthetic random MPS.  Default workload = BASELINE.json configs[3] AS NAMED: batch 4096
+SHARDED over the N ranks (strong scaling: 4096 / 2048 / 1024 / 512 instances per GPU at N = 1/2/4/8,
+contiguous blocks from qsp_b200.distributed.shard_range), results of every rank exchanged by the one
+collective of the path (qsp_b200.distributed.gather_results: a single packed all-gather of overlaps,
+disentangled overlaps, unitaries, kinds, singular values and status).  --batch PER_GPU switches to weak
+scaling (fixed instances per GPU).  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -16,7 +19,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -27,13 +29,13 @@ import numpy as np  # noqa: E402
 from qsp_b200 import flop_model  # noqa: E402
 
 METRIC = "sequential_prep_mps_per_sec"
+UNIT = "MPS/s"
+GEN_BLOCK = 512  # synthetic instances are generated in blocks of this many, seeded by the GLOBAL block index
 _T0 = time.time()
 
 
 def log(msg):
     print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
-
-UNIT = "MPS/s"
 
 
 def parse():
@@ -45,15 +47,25 @@ def parse():
     ap.add_argument("--L", type=int, default=100)
     ap.add_argument("--chi", type=int, default=64)
     ap.add_argument("--layers", type=int, default=4)
-    ap.add_argument("--batch", type=int, default=592, help="instances per GPU per step (4 per SM)")
+    ap.add_argument("--batch-total", type=int, default=None,
+                    help="instances per step over ALL ranks (strong scaling); default 4096 = BASELINE.json configs[3] "
+                         "at the default shape, scaled down by memory for larger shapes")
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU per step (weak scaling) instead of --batch-total")
+    ap.add_argument("--chunk", type=int, default=0, help="instances per qsp_seq_prepare call (0 = by free memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--second-pass", action="store_true")
     ap.add_argument("--workload", default="random", choices=["random", "heisenberg", "aklt"],
                     help="random: SURVEY 8d synthetic MPS; heisenberg: the reference's L=32 ground state "
                          "(tests/golden/heisenberg_L32.npz) replicated over the batch (cfg 3a: --layers 6 --chi 32); "
                          "aklt: make_aklt_mps(L/2) + make_splitted_mps replicated (cfg 3b: --L 100 --layers 6 --chi 32)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None and a.batch_total is None:
+        # configs[3] names 4096 instances of 13.1 MB; keep the resident targets under ~56 GB for other shapes
+        per = a.L * a.chi * a.chi * 32
+        a.batch_total = int(max(a.gpus, min(4096, (56 << 30) // max(per, 1))))
+    return a
 
 
 def workload_name(a):
@@ -79,42 +91,61 @@ def heisenberg_batch(torch, B, chi, dev):
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle (numpy restatement of the reference path; quimb is not installable)
 # --------------------------------------------------------------------------------------
-def cpu_sample(L, chi, layers_sample, n_inst, cores, reps=1, timeout=420, workload="random"):
-    """n_inst instances x layers_sample layers on `cores` single-threaded oracle workers, in a
-    separate interpreter (BLAS threads pinned to 1 through the environment) -> list of wall seconds."""
+def _worker_env():
     env = dict(os.environ)
     for k in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
         env[k] = "1"
     env["CUDA_VISIBLE_DEVICES"] = ""
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_bench_worker.py"), str(L), str(chi), str(layers_sample),
-                          str(n_inst), str(cores), str(reps), workload], env=env, capture_output=True, text=True, timeout=timeout)
+    return env
+
+
+def cpu_sample(L, chi, layers, n_inst, cores, reps=1, timeout=1500, workload="random"):
+    """n_inst instances x `layers` layers on `cores` single-threaded oracle workers, in a separate
+    interpreter (BLAS threads pinned to 1 through the environment) -> list of wall seconds."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_bench_worker.py"), "time", str(L), str(chi),
+                          str(layers), str(n_inst), str(cores), str(reps), workload], env=_worker_env(),
+                         capture_output=True, text=True, timeout=timeout)
     if out.returncode != 0:
         raise RuntimeError(out.stderr[-2000:])
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
 def cpu_cores():
+    """every host core this process may use (nproc workers, the real count is printed)"""
     try:
         n = len(os.sched_getaffinity(0))
     except Exception:  # noqa: BLE001
         n = os.cpu_count() or 1
-    return max(1, min(n, 16))
+    return max(1, n)
 
 
-def cpu_baseline(a):
-    """Bounded sample: one layer of the workload on `cores` instances (one per worker),
-    extrapolated linearly to `layers` layers (with compression on every layer costs the same)."""
+def cpu_baseline(a, parity_npz=None):
+    """Bounded sample: ALL `layers` layers of the workload on `cores` instances (one per single-threaded worker,
+    every host core busy).  With parity_npz (sampled GPU results) the same leg also runs the parity check
+    alongside: the device's unitaries teacher-forced through the oracle."""
     cores = cpu_cores()
-    log(f"cpu_baseline: {cores} oracle workers, 1 layer each ...")
+    log(f"cpu_baseline: {cores} oracle workers (nproc = {cores}), {a.layers} layers each ...")
+    par = None
     try:
-        wall = cpu_sample(a.L, a.chi, 1, cores, cores, workload=a.workload)[0]
+        wall = cpu_sample(a.L, a.chi, a.layers, cores, cores, workload=a.workload)[0]
+        if parity_npz:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_bench_worker.py"), "parity", parity_npz,
+                                  str(cores)], env=_worker_env(), capture_output=True, text=True, timeout=1500)
+            if out.returncode != 0:
+                par = {"ok": False, "error": out.stderr[-300:]}
+            else:
+                par = json.loads(out.stdout.strip().splitlines()[-1])
+                par["tol_overlaps_abs"], par["tol_d2_svals_rel"] = 1e-10, 1e-11
+                par["ok"] = bool(par["max_abs_diff_dis_overlaps"] < 1e-10 and par["max_abs_diff_overlaps"] < 1e-10
+                                 and par["max_rel_diff_d2_svals"] < 1e-11)
+                par["how"] = ("sampled instances of the timed batch: the device's unitaries fed through the oracle's literal "
+                              "reference steps (teacher forcing), per-layer overlaps and D=2 singular values compared")
     except Exception as e:  # noqa: BLE001
-        return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {str(e)[:200]}"}
-    v = cores / (wall * a.layers)
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {str(e)[:200]}"}, par
+    v = cores / wall
     return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} instances x 1 of {a.layers} layers of {workload_name(a)} "
-                      f"(numpy/scipy restatement of the reference path, one single-threaded worker per core, "
-                      f"{wall:.1f}s wall; per-layer cost extrapolated x{a.layers})"}
+            "sample": f"{cores} instances x all {a.layers} layers of {workload_name(a)} (numpy/scipy restatement of the "
+                      f"reference path, one single-threaded worker per host core, nproc = {cores}, {wall:.1f}s wall)"}, par
 
 
 def run_reference(a):
@@ -125,20 +156,31 @@ def run_reference(a):
     steps = max(1, min(a.steps, 3))
     if a.workload == "heisenberg":
         a.L = 32
-    walls = cpu_sample(a.L, a.chi, 1, cores, cores, reps=steps, timeout=900, workload=a.workload)
+    walls = cpu_sample(a.L, a.chi, a.layers, cores, cores, reps=steps, workload=a.workload)
     t = float(np.mean(walls))
-    v = cores / (t * a.layers)
-    sample = (f"each step = {cores} instances x 1 of {a.layers} layers of {workload_name(a)} on {cores} "
-              f"single-threaded workers (numpy/scipy restatement; quimb, the reference's engine, cannot be installed); "
-              f"MPS/s = instances / (wall x {a.layers})")
+    v = cores / t
+    sample = (f"each step = {cores} instances x all {a.layers} layers of {workload_name(a)} on {cores} single-threaded "
+              f"workers = every host core (nproc = {cores}; numpy/scipy restatement -- quimb, the reference's engine, "
+              f"cannot be installed); MPS/s = instances / wall")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    bt = a.batch_total if a.batch is None else a.batch * world
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong" if a.batch is None else "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": {"workload": workload_name(a), "L": a.L, "chi": a.chi, "layers": a.layers},
+        "config": config_dict(a, world, bt, None),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def config_dict(a, world, batch_total, n_local):
+    fm = flop_model.flops_per_mps(a.L, a.chi, a.layers)
+    return {"workload": workload_name(a), "L": a.L, "chi": a.chi, "d": 2, "layers": a.layers, "do_compression": True,
+            "max_bond_dim": a.chi, "batch_total": batch_total,
+            "parallelism": f"batch sharded over {world} rank(s), one packed all-gather of the results",
+            "l2": f"resident targets {batch_total // max(world, 1) * a.L * a.chi * a.chi * 32 / 1e9:.2f} GB per GPU > 126 MB L2 (no flush needed)",
+            "F_ref_flops_per_mps": fm["total"], "B_ref_bytes_per_mps": flop_model.bytes_per_mps(a.L, a.chi, a.layers)}
 
 
 # --------------------------------------------------------------------------------------
@@ -221,6 +263,48 @@ def synth_batch(torch, B, L, chi, dev, seed):
     return x, bonds
 
 
+
+
+def local_inputs(torch, a, dev, b0, b1, want_host):
+    """instances [b0, b1) of the global batch: raw synthetic MPS generated block by block (seed = global block
+    index, so the data of instance i does not depend on the number of ranks), copied to pinned host chunks for
+    the end-to-end leg, then run through the input pipeline (qsp_prepare_target) in place.
+    Returns (prepared targets, bonds, host chunks)."""
+    from qsp_b200.engine import Engine
+
+    eng = Engine(str(dev))
+    n = b1 - b0
+    if a.workload == "heisenberg":
+        raw, bonds = heisenberg_batch(torch, n, a.chi, dev)
+        a.L = raw.shape[1]
+    elif a.workload == "aklt":
+        raw, bonds = aklt_batch(torch, n, a.L, a.chi, dev)
+    else:
+        raw = torch.empty((n, a.L, a.chi, 2, a.chi), dtype=torch.complex128, device=dev)
+        bonds = torch.empty((n, a.L + 1), dtype=torch.int32, device=dev)
+        for blk in range(b0 // GEN_BLOCK, (b1 + GEN_BLOCK - 1) // GEN_BLOCK):
+            g0, g1 = blk * GEN_BLOCK, (blk + 1) * GEN_BLOCK
+            x, bb = synth_batch(torch, GEN_BLOCK, a.L, a.chi, dev, 1234 + blk)
+            lo, hi = max(g0, b0), min(g1, b1)
+            raw[lo - b0:hi - b0] = x[lo - g0:hi - g0]
+            bonds[lo - b0:hi - b0] = bb[lo - g0:hi - g0]
+            del x, bb
+    host = []
+    ck = a.chunk_eff
+    for c0 in range(0, n, ck):
+        c1 = min(n, c0 + ck)
+        if want_host:
+            hm = torch.empty(raw[c0:c1].shape, dtype=raw.dtype, pin_memory=True)
+            hb = torch.empty(bonds[c0:c1].shape, dtype=bonds.dtype, pin_memory=True)
+            hm.copy_(raw[c0:c1])
+            hb.copy_(bonds[c0:c1])
+            host.append((hm, hb))
+        st = eng.prepare_target(raw[c0:c1], bonds[c0:c1])
+        assert int(st.max().item()) & 23 == 0, "prepare_target status"
+    torch.cuda.synchronize()
+    return raw, bonds, host
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -230,6 +314,7 @@ def main():
     import torch.distributed as dist
 
     from qsp_b200 import _runtime
+    from qsp_b200.distributed import gather_results, shard_range
     from qsp_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -241,48 +326,44 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     lib = _runtime.lib()
     eng = Engine(str(dev))
-    B, L, chi, layers = a.batch, a.L, a.chi, a.layers
+    L, chi, layers = a.L, a.chi, a.layers
+    strong = a.batch is None
+    B_total = a.batch_total if strong else a.batch * world
+    b0, b1 = shard_range(B_total, rank, world)
+    n_local = b1 - b0
+    per_inst = L * chi * chi * 32
+    # instances per qsp_seq_prepare call: bounded so that two pipeline slots + a workspace fit beside the targets
+    a.chunk_eff = a.chunk if a.chunk > 0 else int(max(1, min(n_local, 592 if chi >= 64 else 2048, (12 << 30) // per_inst)))
 
-    # ---- inputs resident in HBM (batch * 32 chi^2 L bytes >> 126 MB L2 at the default shape) ----
-    if a.workload == "heisenberg":
-        raw, bonds0 = heisenberg_batch(torch, B, chi, dev)
-        L = a.L = raw.shape[1]
-    elif a.workload == "aklt":
-        raw, bonds0 = aklt_batch(torch, B, L, chi, dev)
-    else:
-        raw, bonds0 = synth_batch(torch, B, L, chi, dev, 1234 + rank)
-    tgt, tb = raw.clone(), bonds0.clone()
-    st = eng.prepare_target(tgt, tb)
-    torch.cuda.synchronize()
-    assert int(st.max().item()) == 0, "prepare_target status"
+    tgt, tb, host = local_inputs(torch, a, dev, b0, b1, want_host=not a.no_e2e)
+    L = a.L
 
     def step():
-        res = eng.seq_prepare(tgt, tb, layers, max_bond=chi, second_pass=a.second_pass)
-        if world > 1:  # the only collective of the path: overlaps + unitaries of every rank
-            ov = [torch.empty_like(res.overlaps) for _ in range(world)]
-            dist.all_gather(ov, res.overlaps)
-            gg = [torch.empty_like(res.G) for _ in range(world)]
-            dist.all_gather(gg, res.G)
-        return res
+        res = eng.seq_prepare(tgt, tb, layers, max_bond=chi, second_pass=a.second_pass, chunk=a.chunk_eff)
+        loc = {"overlaps": res.overlaps, "dis_overlaps": res.dis_overlaps, "G": res.G, "kind": res.kind,
+               "d2_svals": res.d2_svals, "status": res.status}
+        return res, gather_results(loc, B_total)  # world > 1: the only collective of the path
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    log(f"inputs ready: B={B} L={L} chi={chi} layers={layers} world={world}")
+    log(f"inputs ready: batch_total={B_total} local={n_local} chunk={a.chunk_eff} L={L} chi={chi} layers={layers} world={world}")
     for _ in range(a.warmup):
-        res = step()
+        res, full = step()
     barrier()
     log("warm-up done")
-    assert int(res.status.max().item()) == 0, f"device status {res.status.unique().tolist()}"
+    bad = int((full["status"] & 23).max().item())
+    assert bad == 0, f"device status bits {bad:#x}"
+    assert full["G"].shape[1] == B_total and full["overlaps"].shape[1] == B_total
     sampler = ClockSampler(local) if rank == 0 else None
     n0 = lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(a.steps):
-        res = step()
+        res, full = step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -294,48 +375,57 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ms_per_step = ms / a.steps
-    value = world * B / (ms_per_step * 1e-3)
-    ov_last = res.overlaps[layers - 1]
-    assert bool(torch.isfinite(ov_last.abs()).all().item())
+    value = B_total / (ms_per_step * 1e-3)
+    assert bool(torch.isfinite(full["overlaps"][layers - 1].abs()).all().item())
+    n_degenerate = int(((full["status"] & 8) != 0).sum().item())
+
+    # sampled instances for the parity check alongside (rank 0, instances 0 and n_local // 2 of its shard)
+    parity_npz = None
+    if rank == 0 and not a.no_parity and not a.no_cpu_baseline:
+        ks = sorted({0, n_local // 2})
+        parity_npz = os.path.join(tempfile.mkdtemp(prefix="qsp_parity_"), "sample.npz")
+        np.savez(parity_npz, mps=tgt[ks].cpu().numpy(), bonds=tb[ks].cpu().numpy(), G=res.G[:, ks].cpu().numpy(),
+                 kind=res.kind[:, ks].cpu().numpy(), dis=res.dis_overlaps[:, ks].cpu().numpy(),
+                 overlaps=res.overlaps[:, ks].cpu().numpy(), d2_svals=res.d2_svals[:, ks].cpu().numpy(), max_bond=chi)
+    del full
 
     # ---- end-to-end through the public batched API with HOST buffers -----------------------
     e2e = None
     if not a.no_e2e:
-        from qsp_b200.tsp import BatchedMPSPreparation
+        from qsp_b200.tsp import HostBatchPipeline
 
-        host_raw = torch.empty(raw.shape, dtype=raw.dtype, pin_memory=True)
-        host_raw.copy_(raw)
-        host_b = torch.empty(bonds0.shape, dtype=bonds0.dtype, pin_memory=True)
-        host_b.copy_(bonds0)
-        outs = {}
+        pipe = HostBatchPipeline(L, tgt.shape[2], layers, chi, a.chunk_eff, device=str(dev))
+        state = {"out": None}
 
         def e2e_step():
-            d_raw = host_raw.to(dev, non_blocking=True)
-            d_b = host_b.to(dev, non_blocking=True)
-            prep = BatchedMPSPreparation(packed=(d_raw, d_b), device=str(dev))
-            _, r = prep.sequential_unitary_circuit(layers, do_compression=True, max_bond_dim=chi)
-            for k in ("overlaps", "dis_overlaps", "G", "kind", "status"):
-                src = getattr(r, k)
-                if k not in outs:
-                    outs[k] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
-                outs[k].copy_(src, non_blocking=True)
+            # pinned host MPS -> [H2D, prepare_target | layer loop | D2H of the results] pipelined over chunks
+            state["out"] = pipe.run(host, out=state["out"])
+            if world > 1:  # every rank ends up with the overlaps + unitaries of all instances (host side)
+                cat = HostBatchPipeline.concat(state["out"])
+                gather_results({k: v.to(dev, non_blocking=True) for k, v in cat.items()}, B_total)
             torch.cuda.synchronize()
 
         e2e_step()
         barrier()
-        n_e2e = max(1, min(a.steps, 2))
+        n_e2e = 1 if n_local * per_inst > (20 << 30) else max(1, min(a.steps, 2))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             e2e_step()
         barrier()
         dt = (time.perf_counter() - t0) / n_e2e
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        hb = torch.tensor([pipe.h2d_bytes, pipe.d2h_bytes], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(hb, op=dist.ReduceOp.SUM)
         dt = float(tt.item())
-        e2e = {"value": world * B / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(host_raw.numel() * 16 + host_b.numel() * 4),
-               "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in outs.values()))}
+        st_host = HostBatchPipeline.concat(state["out"])["status"]
+        assert int((st_host & 23).max().item()) == 0
+        e2e = {"value": B_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(hb[0].item()),
+               "d2h_bytes_per_step": int(hb[1].item()), "steps": n_e2e,
+               "how": "HostBatchPipeline: pinned host MPS -> H2D + prepare_target of chunk k+1 on a side stream under the layer "
+                      "loop of chunk k, D2H of overlaps/unitaries/kind/status on a third stream; wall clock, max over ranks"}
+        del pipe, state
 
     if rank != 0:
         if world > 1:
@@ -344,20 +434,20 @@ def main():
 
     log(f"e2e done: {e2e}")
     # ---- roofline of the dominant kernel (k_right_compress, 2chi -> chi), timed live --------
-    roof = kernel_roofline(torch, eng, lib, tgt, tb, a, dev)
+    nb = min(n_local, a.chunk_eff)
+    roof = kernel_roofline(torch, eng, lib, tgt[:nb], tb[:nb], a, dev)
     log(f"kernel roofline done: {roof['kernel_ms']:.1f} ms, frac {roof['frac']}")
-    cpu = None if a.no_cpu_baseline else cpu_baseline(a)
-    log("cpu baseline done")
-    fm = flop_model.flops_per_mps(L, chi, layers)
+    cpu, parity = (None, None) if a.no_cpu_baseline else cpu_baseline(a, parity_npz)
+    log(f"cpu baseline done; parity: {parity}")
+    cfg = config_dict(a, world, B_total, n_local)
+    cfg["batch_per_gpu"] = n_local
+    cfg["chunk"] = a.chunk_eff
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "c128", "data": "synthetic",
-        "config": {"workload": workload_name(a), "L": L, "chi": chi, "d": 2, "layers": layers,
-                   "do_compression": True, "max_bond_dim": chi, "batch_per_gpu": B, "parallelism": f"batch-shard x{world}",
-                   "l2": f"inputs {B * L * chi * chi * 32 / 1e9:.2f} GB per GPU > 126 MB L2 (no flush needed)",
-                   "F_ref_flops_per_mps": fm["total"], "B_ref_bytes_per_mps": flop_model.bytes_per_mps(L, chi, layers)},
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "c128", "data": "synthetic", "config": cfg,
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "parity": parity, "degenerate_d2_cuts_reported": n_degenerate,
     }
     print(json.dumps(line))
     if world > 1:
@@ -426,13 +516,22 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
     timed("k_right_compress_d2", lambda: lib.qsp_right_compress(p(psi), p(pb), chi, p(d2), p(d2b), 2, B, L, 2, 1e-10, 1,
                                                                  None, 0, None, p(st), p(work), nb, s))
     timed("k_unitaries", lambda: lib.qsp_generate_unitaries(p(d2), p(d2b), B, L, p(G), p(kind), p(st), s))
+    # second repetition with the per-phase counters on (qsp_set_profile_buffer): sweeps, sites, executed flops
+    prof = torch.zeros((4096, 8), dtype=torch.int64, device=dev)
     reps = []
-    for _ in range(2):
+    for rep in range(2):
+        if rep == 1:
+            lib.qsp_set_profile_buffer(p(prof))
         timed("k_right_compress", lambda: lib.qsp_apply_inverse_and_compress(p(psi), p(pb), p(G), p(kind), p(out), p(ob), chi,
                                                                               B, L, chi, 1e-10, 1, p(amp), p(st), p(work), nb, s))
+        lib.qsp_set_profile_buffer(None)
         reps.append(times["k_right_compress"])
     dur_ms = float(np.mean(reps))
-    fm = flop_model.flops_per_mps(L, chi, 1)
+    pr = prof.sum(dim=0).tolist()
+    executed = float(pr[7])
+    # the model follows the LIVE bond profile of the prepared targets (instance 0), not the nominal chi
+    live = tb[0].tolist()
+    fm = flop_model.flops_per_mps(L, chi, 1, bonds=live)
     # algorithmic flops of what this launch replaces: inverse layer (S2) + re-truncation (S3) + trailing compress (S4)
     alg = B * (fm["S2"] + fm["S3"] + fm["S4"])
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -440,9 +539,9 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
     achieved = alg / (dur_ms * 1e-3) / 1e12
     traffic, traffic_src, ncu_fp64 = None, None, None
     try:  # dram__bytes_read+write of this kernel from the committed ncu capture, scaled to this launch's batch
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("config") == f"L{L} chi{chi} layers4" or tj.get("config") == f"L{L} chi{chi} layers{a.layers}":
+        if tj.get("config") == f"L{L} chi{chi}":
             traffic = tj["dram_bytes_per_instance"] * B
             traffic_src = f"ncu dram__bytes_read.sum+dram__bytes_write.sum at batch {tj['batch']} ({tj['source']}), scaled to batch {B}"
             ncu_fp64 = tj.get("fp64_pipe_busy_pct_ncu")
@@ -450,17 +549,21 @@ def kernel_roofline(torch, eng, lib, tgt, tb, a, dev):
         pass
     layer_ms = sum(v for k, v in times.items())
     return {"bound": "fp64", "kernel": "k_right_compress(fused inverse layer + 2chi->chi)", "achieved": achieved, "peak": peak,
-            "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+            "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+            "executed": executed / (reps[1] * 1e-3) / 1e12, "executed_frac": executed / (reps[1] * 1e-3) / 1e12 / peak if peak else None,
+            "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": "DFMA probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
             "fp64_tensor_peak_dmma_probe": fp64_peak(torch, lib, dev, sms, tensor=True),
-            "note": "achieved counts the REFERENCE's flops this launch replaces (S2+S3+S4 of SURVEY 8d: inverse layer with "
-                    "SVD splits, two 2chi QR sweeps, two SVD sweeps); the device reaches the same state with one Jacobi sweep "
-                    "(DESIGN.md I1-I3), so frac is an algorithmic speed figure, not pipe utilisation",
-            "fp64_pipe_busy_pct_ncu": ncu_fp64,
-            "algorithmic_flops_per_launch": alg, "kernel_ms": dur_ms,
+            "note": "achieved/frac count the REFERENCE's flops this launch replaces (S2+S3+S4 of SURVEY 8d on the live bond "
+                    "profile: inverse layer with SVD splits, two 2chi QR sweeps, two SVD sweeps); the device reaches the same "
+                    "state with one Jacobi sweep (DESIGN.md I1-I3), so frac is an algorithmic speed figure.  executed/"
+                    "executed_frac count the flops the kernel really issues (device counters: Jacobi visits x (16 + 20) flops "
+                    "per column + 8mnk per GEMM) over the same launch = FP64 pipe utilisation",
+            "fp64_pipe_busy_pct_ncu": ncu_fp64, "jacobi_sweeps_per_site": pr[5] / pr[6] if pr[6] else None,
+            "algorithmic_flops_per_launch": alg, "executed_flops_per_launch": executed, "kernel_ms": dur_ms, "batch": B,
             "layer_kernel_ms": {k: round(v, 3) for k, v in times.items()},
             "kernel_share_of_layer": dur_ms / layer_ms if layer_ms else None,
-            "hbm_view": {"achieved_GBps": B * flop_model.bytes_per_mps(L, chi, 1) / (layer_ms * 1e-3) / 1e9,
+            "hbm_view": {"achieved_GBps": B * flop_model.bytes_per_mps(L, chi, 1, bonds=live) / (layer_ms * 1e-3) / 1e9,
                          "peak_GBps": _measured_hbm()}}
 
 

@@ -163,7 +163,7 @@ int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bonds, int B, 
 
 /* Measurement aid (state of the calling host thread): when set (device pointer to >= 8*grid int64, zeroed by the
  * caller), every qsp_right_compress launch issued by this thread adds per-CTA clock64 cycles: [0] A*C GEMM, [1] staging, [2] Jacobi,
- * [3] ranking, [4] Vh/U s, [5] Jacobi sweeps, [6] sites.  NULL (default) disables it. */
+ * [3] ranking, [4] Vh/U s, [5] Jacobi sweeps, [6] sites, [7] floating-point operations executed (Jacobi visits + GEMMs).  NULL (default) disables it. */
 void qsp_set_profile_buffer(void* buf);
 
 #ifdef __cplusplus

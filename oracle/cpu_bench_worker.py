@@ -1,7 +1,9 @@
 """CPU arm of bench.py (TEST / MEASUREMENT INFRASTRUCTURE): times the oracle -- the numpy
-restatement of the reference's sequential path -- on the host cores.
+restatement of the reference's sequential path -- on the host cores, and (parity mode) checks
+sampled GPU results against it.
 
-    python oracle/cpu_bench_worker.py L chi layers n_inst cores reps   -> JSON list of wall seconds
+    python oracle/cpu_bench_worker.py time L chi layers n_inst cores reps workload   -> JSON list of wall seconds
+    python oracle/cpu_bench_worker.py parity sample.npz cores                        -> JSON dict of differences
 
 bench.py starts it in a fresh interpreter with OPENBLAS/OMP threads pinned to 1, so that
 `cores` single-threaded workers do one MPS each."""
@@ -11,7 +13,9 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+WORKLOAD = "random"
 
 
 def one(args):
@@ -21,8 +25,7 @@ def one(args):
     from oracle import qsp_oracle as O
 
     if WORKLOAD == "heisenberg" and L == 32:
-        z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
-                                 "heisenberg_L32.npz"))
+        z = np.load(os.path.join(ROOT, "tests", "golden", "heisenberg_L32.npz"))
         b, m = z["bonds"], z["mps"]
         raw = [m[i, : b[i], :, : b[i + 1]].copy() for i in range(len(b) - 1)]
     elif WORKLOAD == "aklt":
@@ -37,13 +40,67 @@ def one(args):
     return time.time() - t0
 
 
-WORKLOAD = sys.argv[7] if len(sys.argv) > 7 else "random"
+def parity_one(args):
+    """teacher-forced check of one sampled instance: the device's unitaries through the oracle's literal
+    reference steps (sequential.py:45-70); returns the largest differences of the per-layer numbers."""
+    import numpy as np
+
+    from oracle import qsp_oracle as O
+
+    path, k = args
+    z = np.load(path)
+    bonds, mps = z["bonds"][k], z["mps"][k]
+    L = mps.shape[0]
+    tgt = [mps[i, : bonds[i], :, : bonds[i + 1]].copy() for i in range(L)]
+    G, kind = z["G"][:, k], z["kind"][:, k]
+    layers = G.shape[0]
+    gs = []
+    for j in range(layers):
+        out, it = [], 0
+        while it < L:
+            s, g = it, []
+            while True:
+                n = 4 if kind[j, it] == 2 else 2
+                g.append(np.array(G[j, it, :n, :n]))
+                if kind[j, it] == 1:
+                    break
+                it += 1
+            out.append([s, it, g])
+            it += 1
+        gs.append(out)
+    mb = int(z["max_bond"])
+    r = O.sequential_unitary_circuit(tgt, layers, do_compression=True, max_bond_dim=mb, unitaries_override=gs,
+                                     record_svals=True)
+    ev = [i for i in range(layers) if i % 4 == 0 or i == layers - 1]
+    d_dis = float(np.abs(np.array(r["disentangled_mps_overlaps"]) - z["dis"][:, k]).max())
+    d_ov = float(np.abs(np.array(r["overlaps"]) - z["overlaps"][ev, k]).max())
+    d_sv = 0.0
+    for j in range(layers):
+        for q, s in enumerate(r["d2_svals"][j]):
+            i = L - 1 - q
+            n = min(2, len(s))
+            d_sv = max(d_sv, float(np.abs(z["d2_svals"][j, k, i - 1, :n] / s[:n] - 1.0).max()))
+    return {"dis": d_dis, "overlaps": d_ov, "d2_svals_rel": d_sv}
 
 
 def main():
-    L, chi, layers, n_inst, cores, reps = (int(x) for x in sys.argv[1:7])
-    jobs = [(L, chi, layers, 1234 + i) for i in range(n_inst)]
+    global WORKLOAD
+    mode = sys.argv[1]
     ctx = mp.get_context("fork")
+    if mode == "parity":
+        path, cores = sys.argv[2], int(sys.argv[3])
+        import numpy as np
+
+        n = int(np.load(path)["mps"].shape[0])
+        with ctx.Pool(min(cores, n)) as pool:
+            res = pool.map(parity_one, [(path, k) for k in range(n)], chunksize=1)
+        print(json.dumps({"instances": n, "max_abs_diff_dis_overlaps": max(r["dis"] for r in res),
+                          "max_abs_diff_overlaps": max(r["overlaps"] for r in res),
+                          "max_rel_diff_d2_svals": max(r["d2_svals_rel"] for r in res)}))
+        return
+    L, chi, layers, n_inst, cores, reps = (int(x) for x in sys.argv[2:8])
+    WORKLOAD = sys.argv[8] if len(sys.argv) > 8 else "random"
+    jobs = [(L, chi, layers, 1234 + i) for i in range(n_inst)]
     with ctx.Pool(cores) as pool:
         pool.map(one, [(8, 4, 1, 0)] * cores)  # imports / warm-up outside the timed region
         walls = []

@@ -105,8 +105,9 @@ struct LCanonPlan {
 #ifdef QSP_DEV_BUILD  // libqsp_b200_dev.so / the test emulation only (include/qsp_b200_dev.h)
 static int g_force_big = 0;  // test hook (qsp_debug_flags bit 0): take the large-bond path at any size
 static int g_nt_rc = 0, g_nt_lc = 0;  // tuning hooks: threads per CTA of k_right_compress / k_left_canon (0 = planned)
+static int g_enc_cap = 0;             // test hook: padded bond of the encoded-state buffers (0 = QSP_ENC_CAP)
 #else
-static const int g_force_big = 0, g_nt_rc = 0, g_nt_lc = 0;
+static const int g_force_big = 0, g_nt_rc = 0, g_nt_lc = 0, g_enc_cap = 0;
 #endif
 static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
   p->big = false;
@@ -221,6 +222,7 @@ extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, in
 #ifdef QSP_DEV_BUILD
 extern "C" void qsp_debug_flags(int flags) {
   g_force_big = flags & 1;
+  g_enc_cap = ((flags >> 4) & 0xf) ? 1 << ((flags >> 4) & 0xf) : 0;  // bits 4..7: log2 of the encoded-state buffer bond
   g_nt_rc = (flags >> 8) & 0xfff;   // bits 8..19: threads per CTA of k_right_compress
   g_nt_lc = (flags >> 20) & 0xfff;  // bits 20..31: threads per CTA of k_left_canon
 }
@@ -440,11 +442,15 @@ extern "C" int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, i
 // Encoded state U_0..U_k|0..0> (core.py:217-221).  Every forward layer doubles the bonds exactly
 // (k_expand_forward) and keeps the state right canonical and normalised, so the reference's
 // compress('right') after each layer (core.py:140, cutoff only) changes nothing but the bond
-// sizes.  Mode A (layers <= 8): buffers of 2^layers, no compression at all.  Mode B (more layers,
-// short chains with 2^(L/2+1) <= 64): 64-padded buffers, compress whenever the next doubling would
-// not fit (true rank <= 2^(L/2)); chains of 12..15 sites the same way with 256-padded buffers.
+// sizes.  Mode A (2^layers <= QSP_ENC_CAP): buffers of 2^layers, no compression at all.  Mode B (more
+// layers, any chain): like the reference the state is compressed (cutoff only) whenever the next
+// doubling would not fit the De-padded buffers; the compressed bonds must fit De / 2 (QSP_ST_BOND_OVERFLOW
+// otherwise).  The exact rank of an L-site state is at most 2^(L/2), so short chains get by with
+// De = 2^(L/2+1).
+#define QSP_ENC_CAP 256
 struct EncPlan {
   int De;        // padded bond of both encoded-state buffers
+  int rank_cap;  // bound on the bonds after a compression
   bool compress; // mode B
   bool ok;
 };
@@ -452,14 +458,15 @@ static EncPlan plan_enc(int L, int layers) {
   EncPlan e;
   e.ok = true;
   e.compress = false;
-  if (layers <= 8) {
+  const int half = imin(L / 2, 20);
+  const int cap = g_enc_cap ? g_enc_cap : QSP_ENC_CAP;
+  if (layers <= 30 && (1L << layers) <= cap) {
     e.De = 1 << layers;
-  } else if (L / 2 + 1 <= 8) {
-    e.De = (L / 2 + 1 <= 6) ? 64 : 256;
-    e.compress = true;
+    e.rank_cap = e.De;
   } else {
-    e.De = 1;
-    e.ok = false;
+    e.compress = true;
+    e.De = (half + 1 <= 6 && cap >= 64) ? 64 : cap;  // 2^(L/2+1) <= 64: the small kernels take it
+    e.rank_cap = imin(1 << half, e.De / 2);
   }
   return e;
 }
@@ -501,7 +508,7 @@ extern "C" int qsp_encoded_overlap(const qsp_c128* G, const int32_t* kind, int n
   QSP_LAUNCH(k_zero_state, (unsigned)((nl + 127) / 128), 128, 0, st, (cplx*)ea, eab, B, L, De);
   ++g_launches;
   int rc, cur = 1;
-  const int rank_cap = 1 << imin(L / 2, 20);
+  const int rank_cap = e.rank_cap;
   for (int k = n - 1; k >= 0; --k) {
     if (2 * cur > De) {  // mode B: bring the bonds back to the true rank before doubling them again
       if ((rc = left_canonize_live(ea, eab, B, L, De, cur, status, w, sb, stream))) return rc;
@@ -510,8 +517,7 @@ extern "C" int qsp_encoded_overlap(const qsp_c128* G, const int32_t* kind, int n
         return rc;
       qsp_c128* t = ea; ea = eb; eb = t;
       int32_t* tb = eab; eab = ebb; ebb = tb;
-      cur = imin(cur, rank_cap);
-      if (2 * cur > De) return QSP_ERR_UNSUPPORTED;
+      cur = imin(cur, rank_cap);  // a larger true rank was truncated and flagged QSP_ST_BOND_OVERFLOW by the sweep
     }
     const qsp_c128* Gk = G + (size_t)k * B * L * 16;
     const int32_t* kk = kind + (size_t)k * B * L;

@@ -693,6 +693,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
           __syncthreads();
         } else {
           cta_zgemm_deep(2 * b, rp, ro, Ai, Din, 1, false, Cg, DoutL, 1, false, Mg, rp, 1, false, tiles);
+          pc[7] += 8LL * (2 * b) * (rp) * (ro);
         }
       } else if (start && kd[i] == 2) {
         // first site of a multi-site segment: identity embedding, M[l,(a',k)] = C[(l,a'),k]
@@ -718,6 +719,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
             __syncthreads();
           } else {
             cta_zgemm_deep(2 * xe, rp, re, Ai, Din, 1, false, Cg, DoutL, 1, false, Tg, rp, 1, false, tiles);
+          pc[7] += 8LL * (2 * xe) * (rp) * (re);
           }
           // Q[(x,q),k] = sum_p conj(G_i[p][q]) T[(x,p),k]   (G_i^dagger on the physical leg)
           const cplx* ge = Gi + i * 16;
@@ -742,6 +744,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
           for (int bq = 0; bq < 2; ++bq)
             cta_zgemm_deep(2 * lj, rp, xj, Aj, Din, 1, false, Cuse + (long)bq * ldC, 2 * ldC, 1, false, Tg + (long)bq * rp,
                            2L * rp, 1, false, tiles);
+          pc[7] += 16LL * (2 * lj) * rp * xj;
           for (int idx = tid; idx < lj * rp; idx += nt) {
             const int l = idx / rp, k = idx - l * rp;
             cplx pv[4];
@@ -836,6 +839,9 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       QSP_TOCK(2);
       pc[5] += nsweeps;
       pc[6] += 1;
+      // executed flops (bench.py: roofline.executed_frac): a Jacobi visit costs 8 DFMA per Gram column and
+      // 4 DMUL + 8 DFMA per rotated column (16 + 20 flops); the GEMMs of the site count 8 m n k each (QSP_GEMM_FLOPS)
+      pc[7] += (long long)nsweeps * ((long long)nrows * (nrows - 1) / 2) * (16LL * (modeC ? ndotp : len) + 20LL * len);
       // ---- singular values = row norms; rank them ---------------------------------------
       if (io.norms_done) {  // the register path left the squared norms behind
         for (int r = tid; r < nrows; r += nt) norms[r] = sqrt(norms[r]);
@@ -914,6 +920,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
         __syncthreads();
         // U s = M Vh^H
         cta_zgemm_deep(b, k, c, Mg, c, 1, false, Vg, 1, c, true, Cg, DoutL, 1, false, tiles);
+          pc[7] += 8LL * (b) * (k) * (c);
       }
       QSP_TOCK(4);
       // ---- <0...0| amplitude: f_new[q] = sum_kk Vh[q,(0,kk)] f[kk] ---------------------------

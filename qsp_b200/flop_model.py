@@ -60,9 +60,10 @@ def _right_compress(L, b, max_bond):
     return f
 
 
-def flops_per_mps(L, chi, layers, compression=True):
-    """F_ref = layers * (S1 + S2 + S3 + S4) for a random MPS with bond profile min(chi, 2^i, 2^(L-i))."""
-    b = bond_profile(L, chi)
+def flops_per_mps(L, chi, layers, compression=True, bonds=None):
+    """F_ref = layers * (S1 + S2 + S3 + S4) for an MPS with bond profile `bonds` (default: the random-MPS profile
+    min(chi, 2^i, 2^(L-i)); pass the live profile of a structured state so that the model is the work)."""
+    b = [min(int(x), chi) for x in bonds] if bonds is not None else bond_profile(L, chi)
     bp = grown_profile(L, b)
     s1 = _left_canon(L, b) + _right_compress(L, b, 2)
     s2 = 0.0
@@ -75,9 +76,9 @@ def flops_per_mps(L, chi, layers, compression=True):
             "total": layers * (s1 + s2 + s3 + s4)}
 
 
-def bytes_per_mps(L, chi, layers):
+def bytes_per_mps(L, chi, layers, bonds=None):
     """B_ref: every sweep reads and writes every site tensor once."""
-    b = bond_profile(L, chi)
+    b = [min(int(x), chi) for x in bonds] if bonds is not None else bond_profile(L, chi)
     bp = grown_profile(L, b)
     T = sum(32.0 * b[i] * b[i + 1] for i in range(L))
     Tp = sum(32.0 * bp[i] * bp[i + 1] for i in range(L))

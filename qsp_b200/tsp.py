@@ -172,3 +172,92 @@ class BatchedMPSPreparation:
         G = self.seq_data.G[:, b].cpu().numpy()
         kind = self.seq_data.kind[:, b].cpu().numpy()
         return [gates_to_gs_lst(G[k], kind[k]) for k in range(G.shape[0])]
+
+
+class HostBatchPipeline:
+    """End-to-end batched preparation for targets that live in (pinned) HOST memory and are too many to treat as one
+    resident batch: chunks of instances are streamed through the device with the copies hidden under the compute --
+
+        side stream `in` : H2D of chunk k+1 (pinned -> device), MPSPreparation.__init__ pipeline (qsp_prepare_target)
+        main stream      : layer loop of chunk k (qsp_seq_prepare)
+        side stream `out`: D2H of chunk k-1's overlaps / unitaries / kind / status into pinned host buffers
+
+    (the reference's callers loop over instances in Python, examples/benchmarks.py:49-61; this is that loop).
+    Results are host tensors with the layouts of Engine.seq_prepare."""
+
+    KEYS = ("overlaps", "dis_overlaps", "G", "kind", "status")
+
+    def __init__(self, L, D, num_seq_layers, max_bond_dim, chunk, device="cuda:0", overlaps_gap=4):
+        self.dev = torch.device(device)
+        self.L, self.D, self.layers, self.mb, self.chunk, self.gap = L, D, num_seq_layers, int(max_bond_dim), chunk, overlaps_gap
+        self.eng = Engine(device)       # layer loop (main stream)
+        self.eng_in = Engine(device)    # input pipeline (its own workspace: runs concurrently on the side stream)
+        self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.buf = [(torch.empty((chunk, L, D, 2, D), dtype=torch.complex128, device=self.dev),
+                     torch.empty((chunk, L + 1), dtype=torch.int32, device=self.dev),
+                     torch.zeros(chunk, dtype=torch.int32, device=self.dev)) for _ in range(2)]
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _stage_in(self, host_mps, host_bonds, slot, free_ev):
+        m, b, st = self.buf[slot]
+        n = host_mps.shape[0]
+        with torch.cuda.stream(self.s_in):
+            if free_ev is not None:
+                self.s_in.wait_event(free_ev)  # the layer loop that read this slot has finished
+            m[:n].copy_(host_mps, non_blocking=True)
+            b[:n].copy_(host_bonds, non_blocking=True)
+            self.h2d_bytes += host_mps.numel() * 16 + host_bonds.numel() * 4
+            st[:n] = self.eng_in.prepare_target(m[:n], b[:n])
+            ev = torch.cuda.Event()
+            ev.record(self.s_in)
+        return ev
+
+    def run(self, host_chunks, out=None):
+        """host_chunks: list of (mps[n, L, D, 2, D] complex128, bonds[n, L+1] int32) host tensors, n <= chunk
+        (pinned for asynchronous copies).  Returns one dict of pinned, contiguous host tensors (KEYS, layouts of
+        Engine.seq_prepare) PER CHUNK (HostBatchPipeline.concat assembles them); `out` re-uses the buffers of a
+        previous call."""
+        L, layers = self.L, self.layers
+        if out is None:
+            pin = dict(pin_memory=True)
+            out = []
+            for hm, _ in host_chunks:
+                n = hm.shape[0]
+                out.append({"overlaps": torch.empty((layers, n), dtype=torch.complex128, **pin),
+                            "dis_overlaps": torch.empty((layers, n), dtype=torch.complex128, **pin),
+                            "G": torch.empty((layers, n, L, 4, 4), dtype=torch.complex128, **pin),
+                            "kind": torch.empty((layers, n, L), dtype=torch.int32, **pin),
+                            "status": torch.empty((n,), dtype=torch.int32, **pin)})
+        self.h2d_bytes = self.d2h_bytes = 0
+        main = torch.cuda.current_stream(self.dev)
+        free = [None, None]
+        ready = self._stage_in(*host_chunks[0], 0, None)
+        for k, (hm, _) in enumerate(host_chunks):
+            slot = k % 2
+            nxt = None
+            if k + 1 < len(host_chunks):  # next chunk's copy + preparation go under this chunk's layer loop
+                nxt = self._stage_in(*host_chunks[k + 1], 1 - slot, free[1 - slot])
+            main.wait_event(ready)
+            m, b, st = self.buf[slot]
+            n = hm.shape[0]
+            res = self.eng.seq_prepare(m[:n], b[:n], layers, max_bond=self.mb, overlaps_gap=self.gap, chunk=n)
+            res.status |= st[:n]
+            done = torch.cuda.Event()
+            done.record(main)
+            free[slot] = done
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                for key in self.KEYS:
+                    src = getattr(res, key)
+                    src.record_stream(self.s_out)
+                    out[k][key].copy_(src, non_blocking=True)
+                    self.d2h_bytes += src.numel() * src.element_size()
+            ready = nxt
+        self.s_out.synchronize()
+        main.synchronize()
+        return out
+
+    @staticmethod
+    def concat(out):
+        """per-chunk result dicts -> one dict over all instances (host)"""
+        return {k: torch.cat([o[k] for o in out], dim=0 if k == "status" else 1) for k in HostBatchPipeline.KEYS}

@@ -37,3 +37,32 @@ def test_default_workload_is_the_headline_config():
     a = bench.parse()
     assert (a.L, a.chi, a.layers, a.gpus, a.impl) == (100, 64, 4, 1, "b200") and a.warmup >= 3
     assert bench.workload_name(a) == "random_mps_L100_chi64_d2_layers4_compress_maxbond64"
+    # BASELINE.json configs[3] as named: 4096 instances sharded over the ranks (strong scaling) unless --batch is given
+    assert a.batch_total == 4096 and a.batch is None
+
+
+def test_parity_worker_checks_sampled_instances(tmp_path):
+    """the 'parity alongside' leg of bench.py: sampled device results (here: the emulated kernels) teacher-forced
+    through the oracle by oracle/cpu_bench_worker.py"""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import HostDriver, pack_batch
+    from oracle import qsp_oracle as O
+
+    tg = []
+    for s in range(2):
+        t = O.prepare_target(O.random_mps(8, 4, 900 + s), "lpr")
+        O.right_canonize(t, normalize=True)
+        tg.append(t)
+    a, b = pack_batch(tg, 4)
+    r = HostDriver().seq_prepare(a, b, 3, max_bond=4)
+    path = str(tmp_path / "sample.npz")
+    np.savez(path, mps=np.nan_to_num(a), bonds=b, G=r["G"], kind=r["kind"], dis=r["dis"], overlaps=r["overlaps"],
+             d2_svals=r["d2_svals"], max_bond=4)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "cpu_bench_worker.py"), "parity", path, "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["instances"] == 2 and res["max_abs_diff_dis_overlaps"] < 1e-12 and res["max_abs_diff_overlaps"] < 1e-12
+    assert res["max_rel_diff_d2_svals"] < 1e-11

@@ -316,3 +316,28 @@ def test_edge_cases(drv, name):
     assert np.abs(np.array(tf["overlaps"]) - r["overlaps"][ev, 0]).max() < 1e-12
     sc = O.sequential_unitary_circuit(t, layers, completion="canonical", **kw)
     assert [O.unitaries_specs(l) for l in sc["unitaries"]] == [O.unitaries_specs(l) for l in dev_layers]
+
+
+@pytest.mark.parametrize("L,chi,layers,cap_log2,fits", [(12, 2, 6, 4, True), (10, 4, 8, 6, True), (14, 6, 6, 4, False)])
+def test_encoded_state_beyond_buffer_capacity(drv, L, chi, layers, cap_log2, fits):
+    """more layers than the encoded-state buffers can double through (2^layers > cap) on ANY chain: like the
+    reference (core.py:139-141) the encoded state is compressed between layers; a true rank beyond the buffers is
+    truncated and reported as QSP_ST_BOND_OVERFLOW, never silently.  The test hook shrinks the buffers so that the
+    logic of the 256-padded production path runs at emulator-friendly sizes."""
+    drv.lib.qsp_debug_flags(cap_log2 << 4)
+    try:
+        t = _prepared(O.random_mps(L, chi, 5))
+        a, b = pack_batch([t], chi)
+        r = drv.seq_prepare(a, b, layers, max_bond=chi)
+    finally:
+        drv.lib.qsp_debug_flags(0)
+    dl = [gates_to_layers(r["G"][j, 0], r["kind"][j, 0]) for j in range(layers)]
+    tf = O.sequential_unitary_circuit(t, layers, unitaries_override=dl, do_compression=True, max_bond_dim=chi)
+    assert np.abs(np.array(tf["disentangled_mps_overlaps"]) - r["dis"][:, 0]).max() < 1e-12
+    ev = [i for i in range(layers) if i % 4 == 0 or i == layers - 1]
+    if fits:
+        assert r["status"][0] == 0
+        assert np.abs(np.array(tf["overlaps"]) - r["overlaps"][ev, 0]).max() < 1e-12
+    else:
+        assert r["status"][0] == 2  # QSP_ST_BOND_OVERFLOW
+        assert abs(tf["overlaps"][0] - r["overlaps"][0, 0]) < 1e-12  # the evaluations that fitted are still exact
