@@ -139,7 +139,7 @@ def cpu_baseline(a, parity_npz=None):
                 par["ok"] = bool(par["max_abs_diff_dis_overlaps"] < 1e-10 and par["max_abs_diff_overlaps"] < 1e-10
                                  and par["max_rel_diff_d2_svals"] < 1e-11)
                 par["how"] = ("sampled instances of the timed batch: the device's unitaries fed through the oracle's literal "
-                              "reference steps (teacher forcing), per-layer overlaps and D=2 singular values compared")
+                              "reference steps (teacher forcing), per-layer overlaps and the leading D=2 singular value of the first 16 bonds of every layer's sweep compared")
     except Exception as e:  # noqa: BLE001
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {str(e)[:200]}"}, par
     v = cores / wall

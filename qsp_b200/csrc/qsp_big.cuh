@@ -1,0 +1,502 @@
+// Large-bond path (bonds beyond what one SM holds on chip; BASELINE.json configs[4]: chi = 256).
+//
+// The small-bond kernels keep one MPS instance on one SM for a whole sweep.  Here a site matrix (up to
+// 2 chi x 2 chi complex128 = 4 MB at chi = 256) lives in HBM / L2 and EVERY step of a sweep is a batched
+// launch over (instance x tile), so all 148 SMs work whatever the batch size:
+//
+//   k_big_gemm          batched strided complex GEMM on the FP64 tensor cores (DMMA m8n8k4), per-instance
+//                       operand descriptors in device memory
+//   k_big_jacobi_round  one round of a BLOCK one-sided Jacobi SVD: a CTA owns a pair of 16-row blocks of the
+//                       matrix, streams the 32-row panel through shared memory with TMA bulk copies, forms the
+//                       32 x 32 Gram matrix on the tensor cores, factors it (Cholesky), runs one sweep of scalar
+//                       Jacobi rotations on the 32 x 32 factor (accumulating the 32 x 32 unitary J), and applies
+//                       J to the panel as a second tensor-core GEMM.  Pairs follow the round-robin tournament;
+//                       block pairs of one round touch disjoint rows.
+//   k_big_*             elementwise / per-instance helpers of the two sweeps
+//
+// The inner factor keeps the accuracy of Hestenes' method: the Gram entries of two rows are exactly what the
+// scalar method reduces, the Cholesky factor L of G = X X^H has the same row geometry as X (L L^H = G), and
+// the rotations are computed from L (Veselic-Hari), so small rows are resolved relative to their own norms.
+#pragma once
+#include "qsp_common.cuh"
+#include "qsp_jacobi.cuh"
+#include "qsp_mma.cuh"
+
+#define QSP_BIG_RB 16   // rows per Jacobi block
+#define QSP_BIG_PR 32   // rows per block pair (panel)
+#define QSP_BIG_CK 32   // columns per streamed chunk (rows of W are zero-padded to a multiple of it)
+#define QSP_BIG_LDS 34  // shared row stride of a chunk (complex): 4 k-rows x 32 B hit distinct bank groups
+#define QSP_BIG_LDY 68  // shared row stride of Y = [L | J]
+#define QSP_BIG_NS 3    // TMA ring stages
+#define QSP_BIG_NT 256  // threads per CTA of the round and GEMM kernels
+
+// ----------------------------------------------------------------------------------
+// batched GEMM
+// ----------------------------------------------------------------------------------
+struct BigGemm {
+  const cplx* A;
+  const cplx* B;
+  cplx* C;
+  int m, n, k;
+  long sAr, sAk, sBk, sBc, sCr, sCc;
+  int conjA, conjB;
+  int mode;  // 0: C = A B, 1: C += A B, 2: C -= A B
+  int pad;
+};
+
+#define QSP_GB_TM 64
+#define QSP_GB_TN 64
+#define QSP_GB_TK 8
+#define QSP_GB_LD 12  // shared stride of a k-row group: 2 rows x 64 B of a quarter-warp hit distinct banks
+
+__host__ __device__ inline size_t big_gemm_smem_bytes() {
+  return (size_t)2 * (QSP_GB_TM + QSP_GB_TN) * QSP_GB_LD * sizeof(cplx) + 64;
+}
+
+// grid.x = ndesc * tiles_m * tiles_n (tile index fastest); CTAs whose tile lies outside the live extent exit
+__global__ void __launch_bounds__(QSP_BIG_NT) k_big_gemm(const BigGemm* __restrict__ gd, int tiles_m, int tiles_n) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = tiles_m * tiles_n;
+  const int di = blockIdx.x / per, t = blockIdx.x - di * per;
+  const int tm = t / tiles_n, tn = t - tm * tiles_n;
+  const BigGemm g = gd[di];
+  const int i0 = tm * QSP_GB_TM, j0 = tn * QSP_GB_TN;
+  if (g.m <= 0 || g.n <= 0 || i0 >= g.m || j0 >= g.n) return;
+  cplx* sm = (cplx*)QSP_SMEM_BASE();
+  // two buffers of As[64][LD] (element (row, k)) and Bs[64][LD] (element (col, k))
+  cplx* As[2] = {sm, sm + (QSP_GB_TM + QSP_GB_TN) * QSP_GB_LD};
+  cplx* Bs[2] = {As[0] + QSP_GB_TM * QSP_GB_LD, As[1] + QSP_GB_TM * QSP_GB_LD};
+  // loader mapping: 512 elements of A and of B per k-chunk, two of each per thread
+  const bool kfastA = (g.sAk == 1), kfastB = (g.sBk == 1);
+  int ar[2], ak[2], bc[2], bk[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int idx = tid + u * QSP_BIG_NT;
+    if (kfastA) { ak[u] = idx % QSP_GB_TK; ar[u] = idx / QSP_GB_TK; } else { ar[u] = idx % QSP_GB_TM; ak[u] = idx / QSP_GB_TM; }
+    if (kfastB) { bk[u] = idx % QSP_GB_TK; bc[u] = idx / QSP_GB_TK; } else { bc[u] = idx % QSP_GB_TN; bk[u] = idx / QSP_GB_TN; }
+  }
+  cplx ra[2], rb[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      cplx v = cmake(0.0, 0.0);
+      if (i0 + ar[u] < g.m && k0 + ak[u] < g.k) {
+        v = g.A[(long)(i0 + ar[u]) * g.sAr + (long)(k0 + ak[u]) * g.sAk];
+        if (g.conjA) v.y = -v.y;
+      }
+      ra[u] = v;
+      cplx w = cmake(0.0, 0.0);
+      if (j0 + bc[u] < g.n && k0 + bk[u] < g.k) {
+        w = g.B[(long)(k0 + bk[u]) * g.sBk + (long)(j0 + bc[u]) * g.sBc];
+        if (g.conjB) w.y = -w.y;
+      }
+      rb[u] = w;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      As[buf][ar[u] * QSP_GB_LD + ak[u]] = ra[u];
+      Bs[buf][bc[u] * QSP_GB_LD + bk[u]] = rb[u];
+    }
+  };
+  // warp tile: 16 rows x 32 columns = 2 x 4 complex 8x8 tiles; warps 4 (m) x 2 (n)
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;
+  ctile acc[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = ctile_zero();
+  const int fr = lane >> 2, fk = lane & 3;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < g.k; k0 += QSP_GB_TK) {
+    const bool more = k0 + QSP_GB_TK < g.k;
+    if (more) gload(k0 + QSP_GB_TK);
+#pragma unroll
+    for (int ks = 0; ks < QSP_GB_TK; ks += 4) {
+      cplx af[2], bf[4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) af[a] = As[buf][(wm + a * 8 + fr) * QSP_GB_LD + ks + fk];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bf[b] = Bs[buf][(wn + b * 8 + fr) * QSP_GB_LD + ks + fk];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) cdmma(acc[a][b], af[a].x, af[a].y, bf[b].x, bf[b].y);
+    }
+    if (more) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  // epilogue: lane holds rows fr, columns 2 fk + {0, 1} of every tile
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int gi = i0 + wm + a * 8 + fr;
+    if (gi >= g.m) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gj = j0 + wn + b * 8 + 2 * fk + e;
+        if (gj >= g.n) continue;
+        cplx v = cmake(e ? acc[a][b].r1 : acc[a][b].r0, e ? acc[a][b].i1 : acc[a][b].i0);
+        cplx* dst = g.C + (long)gi * g.sCr + (long)gj * g.sCc;
+        if (g.mode == 1) v = cadd(*dst, v);
+        else if (g.mode == 2) v = csub(*dst, v);
+        *dst = v;
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// block Jacobi
+// ----------------------------------------------------------------------------------
+struct BigJac {
+  cplx* W;     // nrows x ldw (row-major); columns [len, ldw) and the Gram padding are zero
+  int nrows;   // rows to orthogonalise
+  int ndotp;   // leading columns that enter the Gram matrix (multiple of QSP_BIG_CK)
+  int len;     // columns to rotate (multiple of QSP_BIG_CK, >= ndotp)
+  int ldw;
+  int nblk;    // number of 16-row blocks, padded to an even number (0: instance inactive)
+  int inner;   // Jacobi sweeps on the 32 x 32 factor per visit
+  double tol2; // rotation threshold on |g|^2 / (alpha beta)
+};
+
+__host__ __device__ inline size_t big_round_smem_bytes() {
+  return (size_t)QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS * sizeof(cplx)  // TMA ring (re-used for the Gram reduction)
+         + (size_t)QSP_BIG_PR * QSP_BIG_LDY * sizeof(cplx)             // Y = [L | J]
+         + 64 * sizeof(double) + QSP_BIG_NS * 16 + 64;
+}
+
+// row r (0..31) of the panel -> row of W, or -1
+__device__ __forceinline__ int big_panel_row(int r, int ra0, int na, int rb0, int nb) {
+  if (r < QSP_BIG_RB) return r < na ? ra0 + r : -1;
+  return (r - QSP_BIG_RB) < nb ? rb0 + (r - QSP_BIG_RB) : -1;
+}
+
+// flags[inst] |= 1 when a rotation above QSP_JAC_QUAD happened (the sweep has to be repeated)
+__global__ void __launch_bounds__(QSP_BIG_NT) k_big_jacobi_round(const BigJac* __restrict__ jd, int* __restrict__ flags, int round,
+                                                                 int pairs_max) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int inst = blockIdx.x / pairs_max, pi = blockIdx.x - inst * pairs_max;
+  const BigJac J = jd[inst];
+  const int nb = J.nblk;
+  if (nb < 2 || pi >= nb / 2 || round >= nb - 1) return;
+  int ba, bb;
+  if (pi == 0) {
+    ba = nb - 1;
+    bb = round;
+  } else {
+    ba = (round + pi) % (nb - 1);
+    bb = (round + nb - 1 - pi) % (nb - 1);
+  }
+  if (ba > bb) {
+    const int t = ba;
+    ba = bb;
+    bb = t;
+  }
+  const int ra0 = ba * QSP_BIG_RB, rb0 = bb * QSP_BIG_RB;
+  const int na = imax(0, imin(QSP_BIG_RB, J.nrows - ra0)), nbr = imax(0, imin(QSP_BIG_RB, J.nrows - rb0));
+  if (na + nbr < 2) return;
+
+  char* smc = QSP_SMEM_BASE();
+  cplx* ring = (cplx*)smc;
+  cplx* Y = ring + QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS;
+  double* sd = (double*)(Y + QSP_BIG_PR * QSP_BIG_LDY);  // [0..31] diagonal of G, [32] max ratio, [33] rotation flag
+  qsp_mbar* bars = (qsp_mbar*)(sd + 64);
+
+  // ---- ring set-up: dead rows stay zero for the whole kernel ------------------------------
+  for (int idx = tid; idx < QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS; idx += QSP_BIG_NT) ring[idx] = cmake(0.0, 0.0);
+  fence_proxy_async();
+  if (tid == 0) {
+    for (int s = 0; s < QSP_BIG_NS; ++s) mbar_init(&bars[s]);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int nlive = na + nbr;
+  const int myrow = (warp == 0) ? big_panel_row(lane, ra0, na, rb0, nbr) : -1;
+  auto issue = [&](int chunk, int stage) {  // warp 0: one bulk copy per live row of the panel
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(&bars[stage], (unsigned)(nlive * QSP_BIG_CK * sizeof(cplx)));
+      __syncwarp();
+      if (myrow >= 0)
+        tma_load_1d(ring + ((long)stage * QSP_BIG_PR + lane) * QSP_BIG_LDS, J.W + (long)myrow * J.ldw + (long)chunk * QSP_BIG_CK,
+                    (unsigned)(QSP_BIG_CK * sizeof(cplx)), &bars[stage]);
+    }
+  };
+  int issued = 0;  // chunks issued so far over both passes (stage = issued % NS, parity = (issued / NS) & 1)
+  int consumed = 0;
+
+  // ---- pass 1: Gram matrix G = X X^H over the Gram columns --------------------------------
+  const int nch1 = J.ndotp / QSP_BIG_CK, nch2 = J.len / QSP_BIG_CK;
+  ctile acc[10];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) acc[t] = ctile_zero();
+  const int fr = lane >> 2, fk = lane & 3;
+  {
+    int next = 0;
+    for (; next < nch1 && next < QSP_BIG_NS - 1; ++next) issue(next, issued++ % QSP_BIG_NS);
+    for (int c = 0; c < nch1; ++c) {
+      if (next < nch1) issue(next++, issued++ % QSP_BIG_NS);
+      const int stage = consumed % QSP_BIG_NS;
+      mbar_wait(&bars[stage], (consumed / QSP_BIG_NS) & 1);
+      ++consumed;
+      const cplx* X = ring + (long)stage * QSP_BIG_PR * QSP_BIG_LDS;
+      // warp w takes k-step w of the chunk (columns 4w .. 4w+3): four row-tile fragments feed all ten tiles
+      cplx f[4];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti) f[ti] = X[(ti * 8 + fr) * QSP_BIG_LDS + warp * 4 + fk];
+      int t = 0;
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < 4; ++tj) cdmma_bh(acc[t++], f[ti].x, f[ti].y, f[tj].x, f[tj].y);
+      __syncthreads();
+    }
+  }
+  // ---- reduce the eight partial Gram matrices (deterministic tree through the idle ring) ---
+  {
+    double* part = (double*)ring;  // [warp][tile][4][32 lanes]
+    for (int half = 4; half >= 1; half >>= 1) {
+      if (warp >= half && warp < 2 * half) {
+        double* p = part + (long)(warp - half) * 10 * 4 * 32;
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+          p[(t * 4 + 0) * 32 + lane] = acc[t].r0;
+          p[(t * 4 + 1) * 32 + lane] = acc[t].r1;
+          p[(t * 4 + 2) * 32 + lane] = acc[t].i0;
+          p[(t * 4 + 3) * 32 + lane] = acc[t].i1;
+        }
+      }
+      __syncthreads();
+      if (warp < half) {
+        const double* p = part + (long)warp * 10 * 4 * 32;
+#pragma unroll
+        for (int t = 0; t < 10; ++t) {
+          acc[t].r0 += p[(t * 4 + 0) * 32 + lane];
+          acc[t].r1 += p[(t * 4 + 1) * 32 + lane];
+          acc[t].i0 += p[(t * 4 + 2) * 32 + lane];
+          acc[t].i1 += p[(t * 4 + 3) * 32 + lane];
+        }
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+      int t = 0;
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < 4; ++tj) {
+          const int r = ti * 8 + fr, c = tj * 8 + 2 * fk;
+          const cplx v0 = cmake(acc[t].r0, acc[t].i0), v1 = cmake(acc[t].r1, acc[t].i1);
+          Y[r * QSP_BIG_LDY + c] = v0;
+          Y[r * QSP_BIG_LDY + c + 1] = v1;
+          if (tj > ti) {
+            Y[c * QSP_BIG_LDY + r] = cconj(v0);
+            Y[(c + 1) * QSP_BIG_LDY + r] = cconj(v1);
+          }
+          ++t;
+        }
+    }
+    __syncthreads();
+    // the ring is the zero-padded TMA target again
+    for (int idx = tid; idx < QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS; idx += QSP_BIG_NT) ring[idx] = cmake(0.0, 0.0);
+    fence_proxy_async();
+  }
+  // ---- convergence of this block pair: max |g_pq|^2 / (g_pp g_qq) ---------------------------
+  if (warp == 0) {
+    const double dp = Y[lane * QSP_BIG_LDY + lane].x;
+    sd[lane] = dp;
+    __syncwarp();
+    double mx = 0.0;
+    for (int q = 0; q < QSP_BIG_PR; ++q) {
+      if (q == lane) continue;
+      const double ab = dp * sd[q];
+      const double g2 = cabs2(Y[lane * QSP_BIG_LDY + q]);
+      if (ab > 1e-280) mx = fmax(mx, g2 / ab);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, shfl_xor_d(mx, o));
+    if (lane == 0) sd[32] = mx;
+  }
+  __syncthreads();
+  const double maxratio = sd[32];
+  if (!(maxratio > J.tol2)) return;  // nothing to rotate in this pair
+  if (tid == 0 && maxratio > QSP_JAC_QUAD * QSP_JAC_QUAD) flags[inst] = 1;
+
+  // ---- Cholesky G = L L^H in place (lower triangle); dependent rows give zero columns -------
+  for (int j = 0; j < QSP_BIG_PR; ++j) {
+    __syncthreads();  // trailing update of column j - 1 done
+    const double piv = Y[j * QSP_BIG_LDY + j].x;
+    const bool ok = piv > 4e-15 * sd[j] && piv > 0.0;
+    const double inv = ok ? qsp_rsqrt(piv) : 0.0;
+    __syncthreads();  // everybody has read the pivot
+    if (tid < QSP_BIG_PR - j) {
+      const int i = j + tid;
+      cplx v = Y[i * QSP_BIG_LDY + j];
+      Y[i * QSP_BIG_LDY + j] = (i == j) ? cmake(ok ? piv * inv : 0.0, 0.0) : cscale(v, inv);
+    }
+    __syncthreads();
+    if (ok) {
+      const int rem = QSP_BIG_PR - 1 - j;
+      for (int idx = tid; idx < rem * rem; idx += QSP_BIG_NT) {
+        const int i = j + 1 + idx / rem, k = j + 1 + idx % rem;
+        if (k <= i) {
+          const cplx li = Y[i * QSP_BIG_LDY + j], lk = Y[k * QSP_BIG_LDY + j];
+          cplx v = Y[i * QSP_BIG_LDY + k];
+          // v -= li * conj(lk)
+          v.x -= li.x * lk.x + li.y * lk.y;
+          v.y -= li.y * lk.x - li.x * lk.y;
+          Y[i * QSP_BIG_LDY + k] = v;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT) {
+    const int i = idx / QSP_BIG_PR, k = idx - i * QSP_BIG_PR;
+    if (k > i) Y[i * QSP_BIG_LDY + k] = cmake(0.0, 0.0);
+    Y[i * QSP_BIG_LDY + QSP_BIG_PR + k] = cmake(i == k ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+
+  // ---- scalar Jacobi on the rows of L, rotations accumulated in J (right half of Y) ----------
+  {
+    const int team = tid >> 4, tl = tid & 15;  // 16 pairs x 16 lanes
+    volatile double* rotflag = sd + 33;
+    for (int sw = 0; sw < J.inner; ++sw) {
+      if (tid == 0) *rotflag = 0.0;
+      __syncthreads();
+      for (int r = 0; r < QSP_BIG_PR - 1; ++r) {
+        int a, b;
+        if (team == 0) {
+          a = QSP_BIG_PR - 1;
+          b = r;
+        } else {
+          a = (r + team) % (QSP_BIG_PR - 1);
+          b = (r + QSP_BIG_PR - 1 - team) % (QSP_BIG_PR - 1);
+        }
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        cplx* xp = Y + p * QSP_BIG_LDY;
+        cplx* yq = Y + q * QSP_BIG_LDY;
+        cplx x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          x[u] = xp[tl + 16 * u];
+          y[u] = yq[tl + 16 * u];
+        }
+        double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          al = fma(x[u].x, x[u].x, fma(x[u].y, x[u].y, al));
+          be = fma(y[u].x, y[u].x, fma(y[u].y, y[u].y, be));
+          gx = fma(x[u].x, y[u].x, fma(x[u].y, y[u].y, gx));
+          gy = fma(x[u].y, y[u].x, fma(-x[u].x, y[u].y, gy));
+        }
+        for (int o = 8; o > 0; o >>= 1) {
+          al += shfl_xor_d(al, o);
+          be += shfl_xor_d(be, o);
+          gx += shfl_xor_d(gx, o);
+          gy += shfl_xor_d(gy, o);
+        }
+        const double g2 = gx * gx + gy * gy, ab = al * be;
+        if (ab > 1e-280 && g2 > J.tol2 * ab) {
+          double cs, sx, sy;
+          jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            cplx xn, yn;
+            xn.x = cs * x[u].x - (sx * y[u].x - sy * y[u].y);
+            xn.y = cs * x[u].y - (sx * y[u].y + sy * y[u].x);
+            yn.x = cs * y[u].x + (sx * x[u].x + sy * x[u].y);
+            yn.y = cs * y[u].y + (sx * x[u].y - sy * x[u].x);
+            xp[tl + 16 * u] = xn;
+            yq[tl + 16 * u] = yn;
+          }
+          if (tl == 0) *rotflag = 1.0;
+        }
+        __syncthreads();
+      }
+      if (*rotflag == 0.0) break;  // (uniform: read after the barrier above)
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2: X <- J X on all columns, J fragments register resident ------------------------
+  {
+    const int rt0 = (warp >> 2) * 2, ct = warp & 3;
+    double jr[2][8], ji[2][8];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const cplx v = Y[((rt0 + t) * 8 + fr) * QSP_BIG_LDY + QSP_BIG_PR + ks * 4 + fk];
+        jr[t][ks] = v.x;
+        ji[t][ks] = v.y;
+      }
+    int orow[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) orow[t] = big_panel_row((rt0 + t) * 8 + fr, ra0, na, rb0, nbr);
+    int next = 0;
+    for (; next < nch2 && next < QSP_BIG_NS - 1; ++next) issue(next, issued++ % QSP_BIG_NS);
+    for (int c = 0; c < nch2; ++c) {
+      if (next < nch2) issue(next++, issued++ % QSP_BIG_NS);
+      const int stage = consumed % QSP_BIG_NS;
+      mbar_wait(&bars[stage], (consumed / QSP_BIG_NS) & 1);
+      ++consumed;
+      const cplx* X = ring + (long)stage * QSP_BIG_PR * QSP_BIG_LDS;
+      ctile o[2] = {ctile_zero(), ctile_zero()};
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const cplx bq = X[(ks * 4 + fk) * QSP_BIG_LDS + ct * 8 + fr];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) cdmma(o[t], jr[t][ks], ji[t][ks], bq.x, bq.y);
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (orow[t] >= 0) {
+          cplx* dst = J.W + (long)orow[t] * J.ldw + (long)c * QSP_BIG_CK + ct * 8 + 2 * fk;
+          dst[0] = cmake(o[t].r0, o[t].i0);
+          dst[1] = cmake(o[t].r1, o[t].i1);
+        }
+      __syncthreads();
+    }
+  }
+}
+
+// after a sweep: converged instances (no rotation above QSP_JAC_QUAD) are retired, *any counts the others
+__global__ void k_big_sweep_end(BigJac* __restrict__ jd, int* __restrict__ flags, int* __restrict__ any, int* __restrict__ sweeps,
+                                int B) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= B) return;
+  if (jd[inst].nblk > 0) {
+    if (sweeps) sweeps[inst] += 1;
+    if (flags[inst] == 0)
+      jd[inst].nblk = 0;
+    else
+      atomicAdd(any, 1);
+    flags[inst] = 0;
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// right compression sweep, large bonds: per-instance state + per-site helper kernels
+// (same mathematics and the same argument block as k_right_compress in qsp_sweeps.cuh)
+// ----------------------------------------------------------------------------------
+struct RCompressArgs;  // qsp_sweeps.cuh
+
+struct BigRCState {
+  int bad, rp, fcur, st;
+  // dims of the current site
+  int b, c, ro, start, kd, modeC, nrows, ndot, ndotp, len, ldw, joff, k;
+  int pad;
+};
+
+// scratch slices of one instance (elements): same partition as the small-bond kernel
+struct BigRCWork {
+  cplx *Mg, *Wg, *Vg, *Cg, *fg;
+};

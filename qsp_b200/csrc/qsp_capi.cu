@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "qsp_sweeps.cuh"
+#include "qsp_big_sweeps.cuh"
 #include "qsp_unitaries.cuh"
 
 #ifdef QSP_EMU
@@ -83,6 +84,17 @@ static void dev_copy(void* dst, const void* src, size_t bytes, qsp_stream_t s) {
   cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
 }
 static void dev_zero(void* dst, size_t bytes, qsp_stream_t s) { cudaMemsetAsync(dst, 0, bytes, s); }
+#endif
+
+#ifdef QSP_EMU
+static int dev_read_int(const int* p, qsp_stream_t) { return *p; }
+#else
+static int dev_read_int(const int* p, qsp_stream_t s) {  // synchronises the stream
+  int v = 0;
+  cudaMemcpyAsync(&v, p, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  return v;
+}
 #endif
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -228,6 +240,123 @@ extern "C" void qsp_debug_flags(int flags) {
 }
 #endif
 
+// ------------------------------------------------------------------------------------
+// large-bond right compression (qsp_big_sweeps.cuh): batched launches per site
+// ------------------------------------------------------------------------------------
+#define QSP_BIG_MAX_SWEEPS 60
+// matrices beyond 128 x 128 no longer fit the register + shared memory of one SM
+static bool rcompress_is_big(int DinL, int DoutL) { return g_force_big || imax(DinL / 2, DoutL) > 64; }
+struct BigRCLayout {
+  size_t off_S, off_jd, off_g1, off_g2, off_gU, off_flags, off_any, off_sweeps, off_work, total;
+  long stride;
+};
+static BigRCLayout big_rc_layout(int B, int DinL, int DoutL) {
+  BigRCLayout l;
+  size_t o = 0;
+  l.off_S = o, o += align_up((size_t)B * sizeof(BigRCState));
+  l.off_jd = o, o += align_up((size_t)B * sizeof(BigJac));
+  l.off_g1 = o, o += align_up((size_t)B * sizeof(BigGemm));
+  l.off_g2 = o, o += align_up((size_t)2 * B * sizeof(BigGemm));
+  l.off_gU = o, o += align_up((size_t)B * sizeof(BigGemm));
+  l.off_flags = o, o += align_up((size_t)B * sizeof(int));
+  l.off_any = o, o += 256;
+  l.off_sweeps = o, o += align_up((size_t)B * sizeof(int));
+  l.off_work = o;
+  l.stride = rcompress_work_elems(DinL, DoutL);
+  l.total = o + align_up((size_t)B * l.stride * sizeof(cplx));
+  return l;
+}
+static int launch_big_gemm(const BigGemm* gd, int ndesc, int m_max, int n_max, qsp_stream_t st) {
+  if (ndesc <= 0 || m_max <= 0 || n_max <= 0) return QSP_OK;
+  const int tm = (m_max + QSP_GB_TM - 1) / QSP_GB_TM, tn = (n_max + QSP_GB_TN - 1) / QSP_GB_TN;
+  QSP_PREP_KERNEL(k_big_gemm, big_gemm_smem_bytes());
+  QSP_LAUNCH(k_big_gemm, ndesc * tm * tn, QSP_BIG_NT, big_gemm_smem_bytes(), st, gd, tm, tn);
+  ++g_launches;
+  return QSP_OK;
+}
+// block Jacobi SVD of the B matrices described by jd (device); nrows_max bounds every instance's row count
+static int big_jacobi_run(BigJac* jd, int B, int nrows_max, int* flags, int* any, int* sweeps, qsp_stream_t st) {
+  if (nrows_max < 2) return QSP_OK;
+  const int nblk = ((nrows_max + QSP_BIG_RB - 1) / QSP_BIG_RB + 1) & ~1;
+  const int pairs = nblk / 2, rounds = nblk - 1;
+  QSP_PREP_KERNEL(k_big_jacobi_round, big_round_smem_bytes());
+  dev_zero(flags, (size_t)B * sizeof(int), st);
+  for (int sw = 0; sw < QSP_BIG_MAX_SWEEPS; ++sw) {
+    dev_zero(any, sizeof(int), st);
+    for (int r = 0; r < rounds; ++r) {
+      QSP_LAUNCH(k_big_jacobi_round, B * pairs, QSP_BIG_NT, big_round_smem_bytes(), st, (const BigJac*)jd, flags, r, pairs);
+      ++g_launches;
+    }
+    QSP_LAUNCH(k_big_sweep_end, (B + 127) / 128, 128, 0, st, jd, flags, any, sweeps, B);
+    ++g_launches;
+    if (dev_read_int(any, st) == 0) break;  // every instance converged (host sync once per sweep)
+  }
+  return check_launch();
+}
+
+static int big_right_compress(const RCompressArgs& a0, void* work, size_t work_bytes, void* stream) {
+  RCompressArgs a = a0;
+  const int B = a.B, L = a.L;
+  BigRCLayout lay = big_rc_layout(B, a.DinL, a.DoutL);
+  if (work_bytes < lay.total) return QSP_ERR_WORKSPACE;
+  char* w = (char*)work;
+  BigRCState* S = (BigRCState*)(w + lay.off_S);
+  BigJac* jd = (BigJac*)(w + lay.off_jd);
+  BigGemm* g1 = (BigGemm*)(w + lay.off_g1);
+  BigGemm* g2 = (BigGemm*)(w + lay.off_g2);
+  BigGemm* gU = (BigGemm*)(w + lay.off_gU);
+  int* flags = (int*)(w + lay.off_flags);
+  int* any = (int*)(w + lay.off_any);
+  int* sweeps = (int*)(w + lay.off_sweeps);
+  a.work = (cplx*)(w + lay.off_work);
+  a.work_stride = lay.stride;
+  a.queue = nullptr;
+  qsp_stream_t st = (qsp_stream_t)stream;
+  const bool fused = a.G != nullptr;
+  const int kmax = (a.max_bond > 0) ? imin(a.max_bond, a.DoutL) : a.DoutL;
+  const int nb1 = (B + 127) / 128;
+  QSP_LAUNCH(k_big_rc_init, nb1, 128, 0, st, a, S);
+  ++g_launches;
+  auto pow2cap = [](int e, int cap) { return e >= 30 ? cap : imin(cap, 1 << e); };
+  int rc;
+  for (int i = L - 1; i >= 0; --i) {
+    // upper bounds of this site's extents: a left-canonical input has bond j <= 2^j, the truncated bond j <= 2^(L-j)
+    const int rp_max = pow2cap(L - 1 - i, kmax);                       // truncated bond i+1
+    const int b_max = pow2cap(i, a.DinL);                              // left extent of the swept state
+    const int c_max = 2 * rp_max;
+    const int lj_max = i > 0 ? pow2cap(i - 1, a.Din) : 1;
+    const int parts = imax(1, imin(64, (int)(((long)b_max * c_max + 4095) / 4096)));
+    QSP_LAUNCH(k_big_rc_site, nb1, 128, 0, st, a, S, i, g1, g2);
+    QSP_LAUNCH(k_big_rc_elem, B * parts, 256, 0, st, a, (const BigRCState*)S, i, 0, parts);
+    g_launches += 2;
+    if ((rc = launch_big_gemm(g1, B, 2 * imin(b_max, a.Din), rp_max, st))) return rc;
+    if (fused) {
+      QSP_LAUNCH(k_big_rc_elem, B * parts, 256, 0, st, a, (const BigRCState*)S, i, 1, parts);
+      ++g_launches;
+      if (i > 0) {
+        if ((rc = launch_big_gemm(g2, 2 * B, 2 * lj_max, rp_max, st))) return rc;
+        QSP_LAUNCH(k_big_rc_elem, B * parts, 256, 0, st, a, (const BigRCState*)S, i, 2, parts);
+        ++g_launches;
+      }
+    }
+    if (i == 0) {
+      QSP_LAUNCH(k_big_rc_final, B, 256, 64 * sizeof(double) + 64, st, a, S);
+      ++g_launches;
+      break;
+    }
+    const int nrows_max = imin(b_max, c_max);
+    QSP_LAUNCH(k_big_rc_jprep, B * parts, 256, 0, st, a, (const BigRCState*)S, jd, parts);
+    ++g_launches;
+    if ((rc = big_jacobi_run(jd, B, nrows_max, flags, any, sweeps, st))) return rc;
+    const size_t rsm = big_rank_smem_bytes(nrows_max);
+    QSP_PREP_KERNEL(k_big_rc_rank, rsm);
+    QSP_LAUNCH(k_big_rc_rank, B, 256, rsm, st, a, S, (const BigJac*)jd, i, gU);
+    ++g_launches;
+    if ((rc = launch_big_gemm(gU, B, b_max, imin(kmax, nrows_max), st))) return rc;
+  }
+  return check_launch();
+}
+
 static int rcompress_grid(int B, const RCompressPlan& p, const DevInfo& d) {
   return grid_for(B, blocks_per_sm((const void*)k_right_compress, p.nt, p.smem), d);
 }
@@ -236,6 +365,8 @@ extern "C" size_t qsp_right_compress_workspace_bytes(int B, int L, int D_in, int
   (void)L;
   DevInfo d = dev_info();
   RCompressPlan p;
+  if (B <= 0 || D_in <= 0 || D_out <= 0) return 0;
+  if (rcompress_is_big(D_in, D_out)) return big_rc_layout(B, D_in, D_out).total;
   if (!plan_rcompress(D_in, D_out, d, &p)) return 0;
 #ifndef QSP_EMU
   QSP_PREP_KERNEL(k_right_compress, p.smem);
@@ -259,6 +390,17 @@ static int right_compress_live(const qsp_c128* in, const int32_t* bonds_in, int 
     DinL = D_in;
   }
   if (DoutL <= 0 || DoutL > D_out) DoutL = D_out;
+  if (rcompress_is_big(DinL, DoutL)) {
+    RCompressArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = (const cplx*)in, a.bonds_in = bonds_in, a.Din = D_in;
+    a.out = (cplx*)out, a.bonds_out = bonds_out, a.Dout = D_out;
+    a.DinL = DinL, a.DoutL = DoutL, a.B = B, a.L = L;
+    a.max_bond = max_bond, a.cutoff = cutoff, a.normalize = normalize;
+    a.svals = svals, a.nsv = nsv, a.amp0 = (cplx*)amp0, a.status = status;
+    a.G = (const cplx*)G, a.kind = kind;
+    return big_right_compress(a, work, work_bytes, stream);
+  }
   DevInfo d = dev_info();
   RCompressPlan p;
   if (!plan_rcompress(DinL, DoutL, d, &p)) return QSP_ERR_UNSUPPORTED;

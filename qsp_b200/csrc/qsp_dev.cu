@@ -4,6 +4,7 @@
 // micro-benchmarks, the shared-memory probe.  The test emulation (tests/emu) is built from this file too.
 #define QSP_DEV_BUILD 1
 #include "qsp_capi.cu"
+#include <vector>
 #include "../../include/qsp_b200_dev.h"
 
 // FP64 throughput probe (bench.py measures the DFMA roofline with it; MEASURED_PEAKS.json
@@ -181,3 +182,73 @@ extern "C" int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int 
   return check_launch();
 }
 
+
+// Block-Jacobi SVD of the large-bond path on its own (tests, micro-benchmarks, ncu): the rows of the B matrices
+// W[B][nrows][ldw] are orthogonalised in place (ldw, ndotp multiples of 32, zero padded); sweeps[B] receives the sweep
+// counts, ok[B] 1 on convergence.  work: B * 64 + 1024 bytes of device memory.
+extern "C" int qsp_big_jacobi(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int* sweeps, int* ok, void* work, void* stream) {
+  if (!W || !sweeps || !ok || !work || B <= 0 || nrows < 1 || ldw % QSP_BIG_CK || ndotp % QSP_BIG_CK || ndotp > ldw) return QSP_ERR_ARG;
+  qsp_stream_t st = (qsp_stream_t)stream;
+  BigJac* jd = (BigJac*)work;
+  int* flags = (int*)((char*)work + align_up((size_t)B * sizeof(BigJac)));
+  int* any = flags + B;
+  std::vector<BigJac> h(B);
+  const double tol = 4e-16 * sqrt((double)ndotp);
+  for (int b = 0; b < B; ++b) {
+    memset(&h[b], 0, sizeof(BigJac));
+    h[b].W = (cplx*)W + (long)b * nrows * ldw;
+    h[b].nrows = nrows, h[b].ndotp = ndotp, h[b].len = ldw, h[b].ldw = ldw;
+    h[b].nblk = nrows >= 2 ? (((nrows + QSP_BIG_RB - 1) / QSP_BIG_RB + 1) & ~1) : 0;
+    h[b].inner = h[b].nblk == 2 ? 8 : 1;
+    h[b].tol2 = tol * tol;
+  }
+#ifdef QSP_EMU
+  memcpy(jd, h.data(), (size_t)B * sizeof(BigJac));
+#else
+  cudaMemcpyAsync(jd, h.data(), (size_t)B * sizeof(BigJac), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+#endif
+  dev_zero(sweeps, (size_t)B * sizeof(int), st);
+  int rc = big_jacobi_run(jd, B, nrows, flags, any, sweeps, st);
+  if (rc) return rc;
+#ifdef QSP_EMU
+  for (int b = 0; b < B; ++b) ok[b] = jd[b].nblk == 0;
+#else
+  cudaMemcpyAsync(h.data(), jd, (size_t)B * sizeof(BigJac), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  std::vector<int> hok(B);
+  for (int b = 0; b < B; ++b) hok[b] = h[b].nblk == 0;
+  cudaMemcpyAsync(ok, hok.data(), (size_t)B * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+#endif
+  return check_launch();
+}
+
+// Batched tensor-core GEMM of the large-bond path on its own: C[b] (m x n, row-major) = op(A[b]) op(B[b]) for B
+// problems of one shape; A is m x k row-major (transA: stored k x m), B is k x n row-major (transB: stored n x k);
+// conj flags conjugate the operand.  work: B * 128 bytes of device memory.
+extern "C" int qsp_big_gemm(const qsp_c128* A, int transA, int conjA, const qsp_c128* Bm, int transB, int conjB, qsp_c128* C, int m,
+                            int n, int k, int batch, void* work, void* stream) {
+  if (!A || !Bm || !C || !work || m <= 0 || n <= 0 || k < 0 || batch <= 0) return QSP_ERR_ARG;
+  qsp_stream_t st = (qsp_stream_t)stream;
+  std::vector<BigGemm> h(batch);
+  for (int b = 0; b < batch; ++b) {
+    BigGemm g;
+    memset(&g, 0, sizeof(g));
+    g.A = (const cplx*)A + (long)b * m * k, g.B = (const cplx*)Bm + (long)b * k * n, g.C = (cplx*)C + (long)b * m * n;
+    g.m = m, g.n = n, g.k = k;
+    g.sAr = transA ? 1 : k, g.sAk = transA ? m : 1;
+    g.sBk = transB ? 1 : n, g.sBc = transB ? k : 1;
+    g.sCr = n, g.sCc = 1;
+    g.conjA = conjA, g.conjB = conjB;
+    h[b] = g;
+  }
+#ifdef QSP_EMU
+  memcpy(work, h.data(), (size_t)batch * sizeof(BigGemm));
+#else
+  cudaMemcpyAsync(work, h.data(), (size_t)batch * sizeof(BigGemm), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+#endif
+  int rc = launch_big_gemm((const BigGemm*)work, batch, m, n, st);
+  return rc ? rc : check_launch();
+}

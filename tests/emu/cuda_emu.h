@@ -50,7 +50,7 @@ struct Block {
   Group bar;
   Group named[16];
   std::vector<Group> warp_bar;
-  std::vector<double> xchg;  // 32 doubles per warp
+  std::vector<double> xchg, xchg2;  // 32 doubles per warp each
   std::function<void()> body;
   unsigned nthreads = 0;
   int cur = -1;
@@ -90,6 +90,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& kernel_call) {
     blk.smem.assign(smem_bytes + 64, 0);
     blk.warp_bar.resize(nt / 32);
     blk.xchg.assign(nt, 0.0);
+    blk.xchg2.assign(nt, 0.0);
     blk.fibers.resize(nt);
     blk.body = [&]() { kernel_call(); };
     g_blk = &blk;
@@ -150,6 +151,21 @@ inline int __shfl_sync(unsigned m, int v, int src, int width = 32) {
 }
 inline int __shfl_xor_sync(unsigned m, int v, int mask, int width = 32) {
   return (int)__shfl_xor_sync(m, (double)v, mask, width);
+}
+// warp-level D(8x8) += A(8x4) B(4x8) with the fragment layout of mma.sync.m8n8k4.f64 (qsp_mma.cuh)
+inline void emu_dmma(double& c0, double& c1, double a, double b) {
+  emu::Block* blk = emu::g_blk;
+  const unsigned t = emu::g_threadIdx.x, w = t / 32, lane = t % 32;
+  blk->xchg[t] = a;
+  blk->xchg2[t] = b;
+  emu::group_sync(blk->warp_bar[w], 32);
+  const unsigned row = lane >> 2, q = lane & 3;
+  for (unsigned k = 0; k < 4; ++k) {
+    const double av = blk->xchg[w * 32 + row * 4 + k];
+    c0 = std::fma(av, blk->xchg2[w * 32 + (2 * q) * 4 + k], c0);
+    c1 = std::fma(av, blk->xchg2[w * 32 + (2 * q + 1) * 4 + k], c1);
+  }
+  emu::group_sync(blk->warp_bar[w], 32);
 }
 inline void __threadfence_block() {}
 inline int atomicAdd(int* p, int v) {

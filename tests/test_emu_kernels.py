@@ -50,7 +50,6 @@ def test_large_bond_left_canonize_path(big_path):
     test_left_canonize(drv)
     test_prepare_target(drv)
     test_layer_loop(drv, "compressed")
-    test_layer_loop(drv, "ten_layers_short_chain")
     assert drv.lib._qsp_left_canonize(drv.p(np.zeros(4 * 2 * 4 * 4, np.complex128)), drv.p(np.ones(5, np.int32)), 1, 4, 4,
                                       None, None, 0, None) == 3  # QSP_ERR_WORKSPACE
 
@@ -341,3 +340,86 @@ def test_encoded_state_beyond_buffer_capacity(drv, L, chi, layers, cap_log2, fit
     else:
         assert r["status"][0] == 2  # QSP_ST_BOND_OVERFLOW
         assert abs(tf["overlaps"][0] - r["overlaps"][0, 0]) < 1e-12  # the evaluations that fitted are still exact
+
+
+# ---------------------------------------------------------------------------------------
+# large-bond path (qsp_big.cuh / qsp_big_sweeps.cuh): tensor-core GEMM, block Jacobi, batched sweep
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k,ta,ca,tb,cb", [(70, 45, 33, 0, 0, 0, 0), (16, 130, 9, 1, 1, 0, 0), (65, 64, 64, 0, 0, 1, 1),
+                                              (3, 5, 0, 0, 0, 0, 0), (100, 7, 50, 1, 0, 1, 0)])
+def test_big_gemm(drv, m, n, k, ta, ca, tb, cb):
+    rng = np.random.default_rng(m + n + k)
+    nb = 2
+    A = rng.standard_normal((nb, m, k)) + 1j * rng.standard_normal((nb, m, k))
+    Bm = rng.standard_normal((nb, k, n)) + 1j * rng.standard_normal((nb, k, n))
+    As = np.ascontiguousarray((A.conj() if ca else A).transpose(0, 2, 1) if ta else (A.conj() if ca else A))
+    Bs = np.ascontiguousarray((Bm.conj() if cb else Bm).transpose(0, 2, 1) if tb else (Bm.conj() if cb else Bm))
+    C = np.full((nb, m, n), np.nan + 0j)
+    work = np.zeros(nb * 128 + 64, np.uint8)
+    drv.lib.qsp_big_gemm(drv.p(As), ta, ca, drv.p(Bs), tb, cb, drv.p(C), m, n, k, nb, drv.p(work), None)
+    assert np.abs(C - A @ Bm).max() < 1e-12 * max(k, 1)
+
+
+@pytest.mark.parametrize("nrows,ndot,extra", [(2, 32, 0), (16, 32, 0), (31, 64, 0), (40, 64, 0), (33, 64, 64)])
+def test_big_block_jacobi(drv, nrows, ndot, extra):
+    """rows of [M | I-ish] orthogonalised: singular values against LAPACK 1e-12, rows orthogonal; graded and
+    rank-deficient inputs included (zero rows / dependent rows hit the Cholesky's zero-pivot branch)."""
+    rng = np.random.default_rng(nrows * 7 + ndot)
+    B = 3 if nrows <= 32 else 2
+    ldw = ndot + extra
+    W = np.zeros((B, nrows, ldw), np.complex128)
+    live = ndot - 5  # the Gram part is zero padded to a multiple of 32
+    for b in range(B):
+        M = rng.standard_normal((nrows, live)) + 1j * rng.standard_normal((nrows, live))
+        if b == 1:
+            M *= (10.0 ** (-6 * rng.random(nrows)))[:, None]  # graded rows
+        if b == B - 1 and nrows > 2:
+            M[1] = M[0] * (0.3 + 0.1j)  # dependent rows
+            M[-1] = 0
+        W[b, :, :live] = M
+        if extra:
+            W[b, :, ndot:ndot + nrows] = np.eye(nrows)
+    W0 = W.copy()
+    sw, ok = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    work = np.zeros(B * 64 + 1024, np.uint8)
+    drv.lib.qsp_big_jacobi(drv.p(W), nrows, ndot, ldw, B, drv.p(sw), drv.p(ok), drv.p(work), None)
+    assert ok.all() and sw.max() <= 20, (ok, sw)
+    for b in range(B):
+        ref = np.linalg.svd(W0[b, :, :ndot], compute_uv=False)
+        nr = np.linalg.norm(W[b, :, :ndot], axis=1)
+        got = np.sort(nr)[::-1]
+        assert np.abs(got - ref).max() < 1e-13 * ref[0] * 10
+        G = W[b, :, :ndot] @ W[b, :, :ndot].conj().T
+        d = np.sqrt(np.abs(np.diag(G)))
+        off = np.abs(G - np.diag(np.diag(G))) / np.maximum(np.outer(d, d), 1e-300)
+        assert off[np.outer(d, d) > 1e-200].max(initial=0) < 1e-13
+        if extra:  # accumulated rotation: W_out = J W_in with J unitary
+            J = W[b, :, ndot:ndot + nrows]
+            assert np.abs(J @ J.conj().T - np.eye(nrows)).max() < 1e-13
+            assert np.abs(J @ W0[b, :, :ndot] - W[b, :, :ndot]).max() < 1e-12 * ref[0]
+
+
+@pytest.mark.parametrize("L,chi,max_bond", [(7, 24, 0), (8, 40, 12)])
+def test_big_right_compress_multiblock(big_path, L, chi, max_bond):
+    """truncating sweep through the batched large-bond kernels with several 16-row blocks per matrix"""
+    drv = big_path
+    mpss = []
+    for s in range(2):
+        m = O.random_mps(L, chi, 20 + s)
+        m[0] = m[0] / np.sqrt(O.inner(m, m).real)
+        mpss.append(O.left_canonize(m))
+    Dout = max_bond if max_bond else chi
+    a, b = pack_batch(mpss, chi)
+    out, bo, st, sv, amp = drv.right_compress(a, b, Dout, max_bond=max_bond, normalize=1, nsv=3, amp0=True)
+    assert st.max() == 0
+    for k, (m, g) in enumerate(zip(mpss, unpack_batch(out, bo))):
+        svl = []
+        ref = O.right_compress(O.copy_mps(m), max_bond=max_bond or None, svals=svl)
+        O.right_canonize(ref, normalize=True)
+        assert O.bonds_of(ref) == O.bonds_of(g)
+        assert abs(abs(O.inner(g, ref)) - 1.0) < 1e-12
+        for j, s in enumerate(svl):
+            i = L - 1 - j
+            n = min(3, len(s))
+            assert np.allclose(sv[k, i - 1, :n], s[:n], rtol=1e-12, atol=1e-14 * s[0])
+        assert abs(amp[k] - O.norm_mps_ovrlap(ref, O.cl_zero_mps(L)) * np.exp(1j * np.angle(O.inner(g, ref)))) < 1e-12
