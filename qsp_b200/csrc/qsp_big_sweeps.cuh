@@ -409,3 +409,311 @@ __global__ void __launch_bounds__(256) k_big_rc_rank(RCompressArgs P, BigRCState
     S[inst] = s;
   }
 }
+
+// ----------------------------------------------------------------------------------
+// left canonisation, large bonds: blocked Householder QR (compact WY), trailing updates and the thin Q as
+// batched tensor-core GEMMs; the panel factorisation is one CTA per instance.
+//   A_i <- thin Q of (R_{i-1} A_i),  R with a non-negative diagonal carried to site i+1  (quimb left_canonize)
+// ----------------------------------------------------------------------------------
+#define QSP_BIG_NBW 16  // panel width
+
+struct BigLCArgs {
+  cplx* mps;        // [B][L][D][2][D], canonised in place
+  int32_t* bonds;   // [B][L+1]
+  int B, L, D, Dm;  // Dm: largest live bond the launch was planned for
+  int32_t* status;
+  cplx* work;       // per-instance scratch, big_lc_work_elems(Dm) each
+  long work_stride;
+};
+struct BigLCState {
+  int bad, a, a_old;
+  int m, n, K;  // current site: S is m x n, K = min(m, n)
+  int pad[2];
+};
+struct BigLCWork {
+  cplx *S, *Q, *V, *VT, *VTh, *Wt, *T, *R, *tau;
+  double* beta;
+  int ldS, ldw;
+};
+__host__ __device__ inline long big_lc_work_elems(int Dm) {
+  const long ldS = 2L * Dm;
+  return 4 * ldS * Dm + ldS * QSP_BIG_NBW + (long)QSP_BIG_NBW * Dm + QSP_BIG_NBW * QSP_BIG_NBW + (long)Dm * Dm + 2L * Dm + 64;
+}
+__device__ __forceinline__ BigLCWork big_lc_work(const BigLCArgs& P, int inst) {
+  BigLCWork w;
+  const long ldS = 2L * P.Dm;
+  w.ldS = (int)ldS;
+  w.ldw = P.Dm;
+  w.S = P.work + (long)inst * P.work_stride;  // m x n, column-major (ldS)
+  w.Q = w.S + ldS * P.Dm;                     // m x K, column-major
+  w.V = w.Q + ldS * P.Dm;                     // explicit reflectors (unit diagonal, zeros above), column-major
+  w.VT = w.V + ldS * P.Dm;                    // V_p T_p of every panel
+  w.VTh = w.VT + ldS * P.Dm;                  // V_p T_p^H of the current panel
+  w.Wt = w.VTh + ldS * QSP_BIG_NBW;           // NBW x n row-major (ldw)
+  w.T = w.Wt + (long)QSP_BIG_NBW * P.Dm;
+  w.R = w.T + QSP_BIG_NBW * QSP_BIG_NBW;      // K x n row-major (ld Dm)
+  w.tau = w.R + (long)P.Dm * P.Dm;
+  w.beta = (double*)(w.tau + P.Dm);
+  return w;
+}
+
+__global__ void k_big_lc_init(BigLCArgs P, BigLCState* __restrict__ S) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= P.B) return;
+  const int32_t* bd = P.bonds + (long)inst * (P.L + 1);
+  bool bad = false;
+  for (int i = 0; i <= P.L; ++i)
+    if (bd[i] > P.Dm || bd[i] < 1) bad = true;
+  BigLCState s;
+  memset(&s, 0, sizeof(s));
+  s.bad = bad ? 1 : 0;
+  s.a = s.a_old = bd[0];
+  S[inst] = s;
+  if (bad && P.status) P.status[inst] |= QSP_ST_BOND_OVERFLOW;
+}
+
+// extents of site i and the operands of S = R A_i (two GEMMs, p = 0, 1)
+__global__ void k_big_lc_site(BigLCArgs P, BigLCState* __restrict__ S, int i, BigGemm* __restrict__ g2) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= P.B) return;
+  BigGemm z;
+  memset(&z, 0, sizeof(z));
+  g2[2 * inst] = g2[2 * inst + 1] = z;
+  BigLCState s = S[inst];
+  if (s.bad) return;
+  const int32_t* bd = P.bonds + (long)inst * (P.L + 1);
+  const int D = P.D;
+  s.m = 2 * s.a;
+  s.n = bd[i + 1];
+  s.K = imin(s.m, s.n);
+  S[inst] = s;
+  if (i == 0) return;  // copied by k_big_lc_elem
+  BigLCWork w = big_lc_work(P, inst);
+  const cplx* Ai = P.mps + ((long)inst * P.L + i) * ((long)D * 2 * D);
+  for (int p = 0; p < 2; ++p) {  // S[(k,p), r] = sum_x R[k,x] A[x,p,r]
+    BigGemm g = z;
+    g.A = w.R, g.sAr = P.Dm, g.sAk = 1;
+    g.B = Ai + (long)p * D, g.sBk = 2L * D, g.sBc = 1;
+    g.C = w.S + p, g.sCr = 2, g.sCc = w.ldS;
+    g.m = s.a, g.n = s.n, g.k = s.a_old;
+    g2[2 * inst + p] = g;
+  }
+}
+
+// phase 0: S <- A_0 (first site);  phase 1: last site, A_{L-1} <- S;  phase 2: R out (sign fixed), Q <- [I; 0];
+// phase 3: A_i <- Q (sign fixed), bonds, carry
+__global__ void __launch_bounds__(256) k_big_lc_elem(BigLCArgs P, BigLCState* __restrict__ S, int i, int phase, int parts) {
+  const int inst = blockIdx.x / parts, part = blockIdx.x - inst * parts;
+  BigLCState s = S[inst];
+  if (s.bad) return;
+  BigLCWork w = big_lc_work(P, inst);
+  const int D = P.D, m = s.m, n = s.n, K = s.K, ldS = w.ldS;
+  cplx* Ai = P.mps + ((long)inst * P.L + i) * ((long)D * 2 * D);
+  const long t0 = (long)part * blockDim.x + threadIdx.x, stride = (long)parts * blockDim.x;
+  if (phase == 0) {
+    for (long idx = t0; idx < (long)m * n; idx += stride) {
+      const int r = (int)(idx / n), c = (int)(idx - (long)r * n);
+      w.S[(long)c * ldS + r] = Ai[(long)r * D + c];
+    }
+  } else if (phase == 1) {
+    for (long idx = t0; idx < (long)m * n; idx += stride) {
+      const int r = (int)(idx / n), c = (int)(idx - (long)r * n);
+      Ai[(long)r * D + c] = w.S[(long)c * ldS + r];
+    }
+  } else if (phase == 2) {
+    for (long idx = t0; idx < (long)K * n; idx += stride) {
+      const int r = (int)(idx / n), c = (int)(idx - (long)r * n);
+      cplx v = cmake(0.0, 0.0);
+      if (c == r)
+        v = cmake(w.beta[r], 0.0);
+      else if (c > r)
+        v = w.S[(long)c * ldS + r];
+      if (w.beta[r] < 0.0) v = cmake(-v.x, -v.y);
+      w.R[(long)r * P.Dm + c] = v;
+    }
+    for (long idx = t0; idx < (long)m * K; idx += stride) {
+      const int c = (int)(idx / m), r = (int)(idx - (long)c * m);
+      w.Q[(long)c * ldS + r] = cmake(r == c ? 1.0 : 0.0, 0.0);
+    }
+  } else {
+    for (long idx = t0; idx < (long)m * K; idx += stride) {
+      const int r = (int)(idx / K), c = (int)(idx - (long)r * K);
+      const cplx q = w.Q[(long)c * ldS + r];
+      Ai[(long)r * D + c] = w.beta[c] < 0.0 ? cmake(-q.x, -q.y) : q;
+    }
+    if (part == 0 && threadIdx.x == 0) {
+      int32_t* bd = P.bonds + (long)inst * (P.L + 1);
+      bd[i] = s.a;
+      bd[i + 1] = K;
+      s.a = K;
+      s.a_old = n;
+      S[inst] = s;
+    }
+  }
+}
+
+// Householder factorisation of the panel S[p0:m, p0:p0+jb] (in place, zgeqr2 conventions: H_j = I - tau_j v_j v_j^H,
+// v_j[j] = 1, real diagonal beta_j), the triangular factor T of the compact WY form Q_p = H_1..H_jb = I - V T V^H,
+// explicit V, V T and V T^H for the GEMMs, and the operands of the trailing update
+//   C <- C - (V T^H) (V^H C),   C = S[p0:m, p0+jb:n].      One CTA per instance.
+__global__ void __launch_bounds__(256) k_big_qr_panel(BigLCArgs P, const BigLCState* __restrict__ Sst, int p0, BigGemm* __restrict__ gW,
+                                                      BigGemm* __restrict__ gC) {
+  const int inst = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  BigGemm z;
+  memset(&z, 0, sizeof(z));
+  const BigLCState s = Sst[inst];
+  if (s.bad || p0 >= s.K) {
+    if (tid == 0) gW[inst] = gC[inst] = z;
+    return;
+  }
+  double* red = (double*)QSP_SMEM_BASE();       // 64 doubles
+  cplx* Z = (cplx*)(red + 64);                  // NBW x NBW Gram of the reflectors
+  cplx* Ts = Z + QSP_BIG_NBW * QSP_BIG_NBW;     // NBW x NBW
+  BigLCWork w = big_lc_work(P, inst);
+  const int m = s.m, n = s.n, K = s.K, ldS = w.ldS;
+  const int jb = imin(QSP_BIG_NBW, K - p0);
+  const int mm = m - p0;                        // rows of the panel
+  cplx* Pn = w.S + (long)p0 * ldS + p0;         // panel, column-major
+  for (int j = 0; j < jb; ++j) {
+    cplx* col = Pn + (long)j * ldS;
+    // ---- reflector j from rows j .. mm-1 of column j ----
+    double xn2 = 0.0;
+    for (int r = j + 1 + tid; r < mm; r += nt) xn2 += cabs2(col[r]);
+    xn2 = block_sum(xn2, red);
+    const cplx alpha = col[j];
+    cplx t, sc = cmake(0.0, 0.0);
+    double bt;
+    if (xn2 == 0.0 && alpha.y == 0.0) {
+      t = cmake(0.0, 0.0);
+      bt = alpha.x;
+    } else {
+      const double nrm = sqrt(cabs2(alpha) + xn2);
+      bt = alpha.x >= 0.0 ? -nrm : nrm;
+      const double ibt = 1.0 / bt;
+      t = cmake((bt - alpha.x) * ibt, -alpha.y * ibt);
+      const double dx = alpha.x - bt;
+      const double id2 = 1.0 / fma(dx, dx, alpha.y * alpha.y);
+      sc = cmake(dx * id2, -alpha.y * id2);  // 1 / (alpha - beta)
+    }
+    __syncthreads();  // everybody has read alpha
+    if (t.x != 0.0 || t.y != 0.0)
+      for (int r = j + 1 + tid; r < mm; r += nt) col[r] = cmul(col[r], sc);
+    if (tid == 0) {
+      w.tau[p0 + j] = t;
+      w.beta[p0 + j] = bt;
+      col[j] = cmake(bt, 0.0);
+    }
+    __syncthreads();
+    // ---- H_j^H on the remaining panel columns: one warp per column ----
+    if (t.x != 0.0 || t.y != 0.0) {
+      const cplx f = cconj(t);
+      for (int c = j + 1 + warp; c < jb; c += nw) {
+        cplx* cc = Pn + (long)c * ldS;
+        cplx wv = cmake(0.0, 0.0);
+        for (int r = j + lane; r < mm; r += 32) {
+          const cplx v = (r == j) ? cmake(1.0, 0.0) : col[r];
+          cfma_conja(wv, v, cc[r]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          wv.x += shfl_xor_d(wv.x, o);
+          wv.y += shfl_xor_d(wv.y, o);
+        }
+        const cplx g = cmul(f, wv);
+        for (int r = j + lane; r < mm; r += 32) {
+          const cplx v = (r == j) ? cmake(1.0, 0.0) : col[r];
+          cc[r] = csub(cc[r], cmul(g, v));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- explicit V (mm x jb) ----
+  cplx* Vp = w.V + (long)p0 * ldS + p0;
+  for (int idx = tid; idx < mm * jb; idx += nt) {
+    const int j = idx / mm, r = idx - j * mm;
+    Vp[(long)j * ldS + r] = (r == j) ? cmake(1.0, 0.0) : (r > j ? Pn[(long)j * ldS + r] : cmake(0.0, 0.0));
+  }
+  __syncthreads();
+  // ---- Z = V^H V (upper part), T by the forward recurrence ----
+  for (int pr = warp; pr < jb * jb; pr += nw) {
+    const int a = pr / jb, b = pr - a * jb;
+    if (a >= b) continue;
+    cplx acc = cmake(0.0, 0.0);
+    for (int r = b + lane; r < mm; r += 32) cfma_conja(acc, Vp[(long)a * ldS + r], Vp[(long)b * ldS + r]);
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.x += shfl_xor_d(acc.x, o);
+      acc.y += shfl_xor_d(acc.y, o);
+    }
+    if (lane == 0) Z[a * QSP_BIG_NBW + b] = acc;
+  }
+  for (int idx = tid; idx < QSP_BIG_NBW * QSP_BIG_NBW; idx += nt) Ts[idx] = cmake(0.0, 0.0);
+  __syncthreads();
+  for (int j = 0; j < jb; ++j) {
+    const cplx tj = w.tau[p0 + j];
+    if (tid < j) {  // T[i][j] = -tau_j sum_{l=i}^{j-1} T[i][l] Z[l][j]
+      cplx acc = cmake(0.0, 0.0);
+      for (int l = tid; l < j; ++l) cfma(acc, Ts[tid * QSP_BIG_NBW + l], Z[l * QSP_BIG_NBW + j]);
+      Ts[tid * QSP_BIG_NBW + j] = cmul(cmake(-tj.x, -tj.y), acc);
+    } else if (tid == j) {
+      Ts[j * QSP_BIG_NBW + j] = tj;
+    }
+    __syncthreads();
+  }
+  // ---- V T and V T^H ----
+  cplx* VTp = w.VT + (long)p0 * ldS + p0;
+  for (int idx = tid; idx < mm * jb; idx += nt) {
+    const int j = idx / mm, r = idx - j * mm;
+    cplx a1 = cmake(0.0, 0.0), a2 = cmake(0.0, 0.0);
+    for (int l = 0; l < jb; ++l) {
+      const cplx v = Vp[(long)l * ldS + r];
+      if (l <= j) cfma(a1, v, Ts[l * QSP_BIG_NBW + j]);
+      if (l >= j) cfma(a2, v, cconj(Ts[j * QSP_BIG_NBW + l]));
+    }
+    VTp[(long)j * ldS + r] = a1;
+    w.VTh[(long)j * ldS + r] = a2;
+  }
+  if (tid == 0) {
+    BigGemm g = z, h = z;
+    const int ntr = n - (p0 + jb);
+    if (ntr > 0) {
+      cplx* C = w.S + (long)(p0 + jb) * ldS + p0;
+      g.A = Vp, g.sAr = ldS, g.sAk = 1, g.conjA = 1;  // W = V^H C
+      g.B = C, g.sBk = 1, g.sBc = ldS;
+      g.C = w.Wt, g.sCr = w.ldw, g.sCc = 1;
+      g.m = jb, g.n = ntr, g.k = mm;
+      h.A = w.VTh, h.sAr = 1, h.sAk = ldS;            // C -= (V T^H) W
+      h.B = w.Wt, h.sBk = w.ldw, h.sBc = 1;
+      h.C = C, h.sCr = 1, h.sCc = ldS;
+      h.m = mm, h.n = ntr, h.k = jb, h.mode = 2;
+    }
+    gW[inst] = g;
+    gC[inst] = h;
+  }
+}
+
+// operands of the backward accumulation of the thin Q for panel p0:  Q[p0:m, p0:K] -= (V T) (V^H Q[p0:m, p0:K])
+__global__ void k_big_lc_qdesc(BigLCArgs P, const BigLCState* __restrict__ S, int p0, BigGemm* __restrict__ gW, BigGemm* __restrict__ gC) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= P.B) return;
+  BigGemm g, h;
+  memset(&g, 0, sizeof(g));
+  memset(&h, 0, sizeof(h));
+  const BigLCState s = S[inst];
+  if (!s.bad && p0 < s.K) {
+    BigLCWork w = big_lc_work(P, inst);
+    const int ldS = w.ldS, jb = imin(QSP_BIG_NBW, s.K - p0), mm = s.m - p0, nc = s.K - p0;
+    cplx* Vp = w.V + (long)p0 * ldS + p0;
+    cplx* VTp = w.VT + (long)p0 * ldS + p0;
+    cplx* Qs = w.Q + (long)p0 * ldS + p0;
+    g.A = Vp, g.sAr = ldS, g.sAk = 1, g.conjA = 1;
+    g.B = Qs, g.sBk = 1, g.sBc = ldS;
+    g.C = w.Wt, g.sCr = w.ldw, g.sCc = 1;
+    g.m = jb, g.n = nc, g.k = mm;
+    h.A = VTp, h.sAr = 1, h.sAk = ldS;
+    h.B = w.Wt, h.sBk = w.ldw, h.sBc = 1;
+    h.C = Qs, h.sCr = 1, h.sCc = ldS;
+    h.m = mm, h.n = nc, h.k = jb, h.mode = 2;
+  }
+  gW[inst] = g;
+  gC[inst] = h;
+}

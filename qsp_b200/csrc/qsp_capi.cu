@@ -112,7 +112,7 @@ static int grid_for(int B, int per_sm, const DevInfo& d) {
 struct LCanonPlan {
   int nt;
   size_t smem;
-  bool big;  // site matrix in the L2-resident scratch (k_left_canon_big)
+  bool big;  // bonds beyond one SM's shared memory: batched blocked-Householder path (big_left_canonize)
 };
 #ifdef QSP_DEV_BUILD  // libqsp_b200_dev.so / the test emulation only (include/qsp_b200_dev.h)
 static int g_force_big = 0;  // test hook (qsp_debug_flags bit 0): take the large-bond path at any size
@@ -123,6 +123,8 @@ static const int g_force_big = 0, g_nt_rc = 0, g_nt_lc = 0, g_enc_cap = 0;
 #endif
 static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
   p->big = false;
+  p->nt = 256;
+  p->smem = 0;
   if (2 * D <= 32 * QSP_QR_MAXR && !g_force_big) {  // a column must fit one warp's registers
     p->nt = D <= 8 ? 64 : (D <= 24 ? 128 : (D <= 48 ? 256 : 512));  // measured at chi = 8, 16, 32, 64
     if (g_nt_lc) p->nt = g_nt_lc;
@@ -133,15 +135,11 @@ static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
     }
     if (p->smem <= d.max_smem) return true;
   }
-  if (2 * D > 32 * QSP_QR_MAXR_BIG) return false;
-  p->big = true;
-  p->nt = D <= 8 ? 64 : (D <= 32 ? 128 : 256);
-  p->smem = lcanon_smem_bytes_big(D, p->nt);
-  return p->smem <= d.max_smem;
+  p->big = true;  // batched blocked-Householder path (qsp_big_sweeps.cuh): any bond
+  return true;
 }
 static int lcanon_grid(int B, const LCanonPlan& p, const DevInfo& d) {
-  const void* k = p.big ? (const void*)k_left_canon_big : (const void*)k_left_canon;
-  return grid_for(B, blocks_per_sm(k, p.nt, p.smem), d);
+  return grid_for(B, blocks_per_sm((const void*)k_left_canon, p.nt, p.smem), d);
 }
 
 struct RCompressPlan {
@@ -196,15 +194,92 @@ extern "C" long long qsp_launch_count(void) { return g_launches; }
 
 // Dlive: largest bond that can occur in this call (<= D, the padded stride); the launch (threads,
 // shared memory, CTAs per SM) is planned for Dlive, a larger live bond sets QSP_ST_BOND_OVERFLOW.
+// ------------------------------------------------------------------------------------
+// large-bond left canonisation (qsp_big_sweeps.cuh): blocked Householder QR, batched launches per site
+// ------------------------------------------------------------------------------------
+struct BigLCLayout {
+  size_t off_S, off_g2, off_gW, off_gC, off_work, total;
+  long stride;
+};
+static BigLCLayout big_lc_layout(int B, int Dm) {
+  BigLCLayout l;
+  size_t o = 0;
+  l.off_S = o, o += align_up((size_t)B * sizeof(BigLCState));
+  l.off_g2 = o, o += align_up((size_t)2 * B * sizeof(BigGemm));
+  l.off_gW = o, o += align_up((size_t)B * sizeof(BigGemm));
+  l.off_gC = o, o += align_up((size_t)B * sizeof(BigGemm));
+  l.off_work = o;
+  l.stride = big_lc_work_elems(Dm);
+  l.total = o + align_up((size_t)B * l.stride * sizeof(cplx));
+  return l;
+}
+static int launch_big_gemm(const BigGemm* gd, int ndesc, int m_max, int n_max, qsp_stream_t st);
+static int big_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int Dm, int32_t* status, void* work,
+                             size_t work_bytes, void* stream) {
+  BigLCLayout lay = big_lc_layout(B, Dm);
+  if (!work || work_bytes < lay.total) return QSP_ERR_WORKSPACE;
+  char* w = (char*)work;
+  BigLCState* S = (BigLCState*)(w + lay.off_S);
+  BigGemm* g2 = (BigGemm*)(w + lay.off_g2);
+  BigGemm* gW = (BigGemm*)(w + lay.off_gW);
+  BigGemm* gC = (BigGemm*)(w + lay.off_gC);
+  BigLCArgs a;
+  a.mps = (cplx*)mps, a.bonds = bonds, a.B = B, a.L = L, a.D = D, a.Dm = Dm, a.status = status;
+  a.work = (cplx*)(w + lay.off_work), a.work_stride = lay.stride;
+  qsp_stream_t st = (qsp_stream_t)stream;
+  const int nb1 = (B + 127) / 128;
+  const size_t psm = 64 * sizeof(double) + 2 * QSP_BIG_NBW * QSP_BIG_NBW * sizeof(cplx) + 64;
+  QSP_LAUNCH(k_big_lc_init, nb1, 128, 0, st, a, S);
+  ++g_launches;
+  int rc;
+  for (int i = 0; i < L; ++i) {
+    // upper bounds: the new left bond of site i is at most 2^i
+    const int a_max = i >= 30 ? Dm : imin(Dm, 1 << i);
+    const int m_max = 2 * a_max, n_max = Dm, K_max = imin(m_max, n_max);
+    const int parts = imax(1, imin(64, (int)(((long)m_max * n_max + 4095) / 4096)));
+    QSP_LAUNCH(k_big_lc_site, nb1, 128, 0, st, a, S, i, g2);
+    ++g_launches;
+    if (i == 0) {
+      QSP_LAUNCH(k_big_lc_elem, B * parts, 256, 0, st, a, S, i, 0, parts);
+      ++g_launches;
+    } else if ((rc = launch_big_gemm(g2, 2 * B, a_max, n_max, st))) {
+      return rc;
+    }
+    if (i == L - 1) {
+      QSP_LAUNCH(k_big_lc_elem, B * parts, 256, 0, st, a, S, i, 1, parts);
+      ++g_launches;
+      break;
+    }
+    for (int p0 = 0; p0 < K_max; p0 += QSP_BIG_NBW) {
+      QSP_LAUNCH(k_big_qr_panel, B, 256, psm, st, a, (const BigLCState*)S, p0, gW, gC);
+      ++g_launches;
+      if (n_max - p0 - 1 > 0) {  // (a wide site, K < n, has trailing columns behind a short last panel)
+        if ((rc = launch_big_gemm(gW, B, QSP_BIG_NBW, n_max - p0 - 1, st))) return rc;
+        if ((rc = launch_big_gemm(gC, B, m_max - p0, n_max - p0 - 1, st))) return rc;
+      }
+    }
+    QSP_LAUNCH(k_big_lc_elem, B * parts, 256, 0, st, a, S, i, 2, parts);
+    ++g_launches;
+    for (int p0 = (K_max - 1) / QSP_BIG_NBW * QSP_BIG_NBW; p0 >= 0; p0 -= QSP_BIG_NBW) {
+      QSP_LAUNCH(k_big_lc_qdesc, nb1, 128, 0, st, a, (const BigLCState*)S, p0, gW, gC);
+      ++g_launches;
+      if ((rc = launch_big_gemm(gW, B, QSP_BIG_NBW, K_max - p0, st))) return rc;
+      if ((rc = launch_big_gemm(gC, B, m_max - p0, K_max - p0, st))) return rc;
+    }
+    QSP_LAUNCH(k_big_lc_elem, B * parts, 256, 0, st, a, S, i, 3, parts);
+    ++g_launches;
+  }
+  return check_launch();
+}
+
+// Dlive: largest bond that can occur in this call (<= D, the padded stride); the launch (threads,
+// shared memory, CTAs per SM) is planned for Dlive, a larger live bond sets QSP_ST_BOND_OVERFLOW.
 extern "C" size_t qsp_left_canonize_workspace_bytes(int B, int L, int D) {
   (void)L;
   DevInfo d = dev_info();
   LCanonPlan p;
   if (B <= 0 || D <= 0 || !plan_lcanon(D, d, &p) || !p.big) return 0;
-#ifndef QSP_EMU
-  QSP_PREP_KERNEL(k_left_canon_big, p.smem);
-#endif
-  return align_up((size_t)lcanon_grid(B, p, d) * lcanon_work_elems(D) * sizeof(cplx));
+  return big_lc_layout(B, D).total;
 }
 static int left_canonize_live(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int Dlive, int32_t* status,
                               void* work, size_t work_bytes, void* stream) {
@@ -213,17 +288,10 @@ static int left_canonize_live(qsp_c128* mps, int32_t* bonds, int B, int L, int D
   DevInfo d = dev_info();
   LCanonPlan p;
   if (!plan_lcanon(Dlive, d, &p)) return QSP_ERR_UNSUPPORTED;
-  if (p.big) {
-    QSP_PREP_KERNEL(k_left_canon_big, p.smem);
-    int grid = lcanon_grid(B, p, d);
-    if (!work || work_bytes < (size_t)grid * lcanon_work_elems(Dlive) * sizeof(cplx)) return QSP_ERR_WORKSPACE;
-    QSP_LAUNCH(k_left_canon_big, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, Dlive, status,
-               g_prof, (cplx*)work);
-  } else {
-    QSP_PREP_KERNEL(k_left_canon, p.smem);
-    int grid = lcanon_grid(B, p, d);
-    QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, Dlive, status, g_prof);
-  }
+  if (p.big) return big_left_canonize(mps, bonds, B, L, D, Dlive, status, work, work_bytes, stream);
+  QSP_PREP_KERNEL(k_left_canon, p.smem);
+  int grid = lcanon_grid(B, p, d);
+  QSP_LAUNCH(k_left_canon, grid, p.nt, p.smem, (qsp_stream_t)stream, (cplx*)mps, bonds, B, L, D, Dlive, status, g_prof);
   ++g_launches;
   return check_launch();
 }

@@ -547,13 +547,6 @@ __global__ void __launch_bounds__(512) k_left_canon(cplx* __restrict__ mps, int3
                                                     int Dm, int32_t* __restrict__ status, long long* prof) {
   left_canon_impl<false>(mps, bonds, B, L, D, Dm, status, prof, nullptr);
 }
-// large bonds (the site matrix does not fit shared memory): same sweep out of an L2-resident scratch
-__global__ void __launch_bounds__(256, 1) k_left_canon_big(cplx* __restrict__ mps, int32_t* __restrict__ bonds, int B, int L,
-                                                        int D, int Dm, int32_t* __restrict__ status, long long* prof,
-                                                        cplx* gwork) {
-  left_canon_impl<true>(mps, bonds, B, L, D, Dm, status, prof, gwork);
-}
-
 // ----------------------------------------------------------------------------------
 // right compression (truncating SVD sweep) of a left-canonical MPS
 // ----------------------------------------------------------------------------------

@@ -423,3 +423,30 @@ def test_big_right_compress_multiblock(big_path, L, chi, max_bond):
             n = min(3, len(s))
             assert np.allclose(sv[k, i - 1, :n], s[:n], rtol=1e-12, atol=1e-14 * s[0])
         assert abs(amp[k] - O.norm_mps_ovrlap(ref, O.cl_zero_mps(L)) * np.exp(1j * np.angle(O.inner(g, ref)))) < 1e-12
+
+
+def test_big_left_canonize_multipanel(big_path):
+    """blocked Householder QR of the large-bond path with several 16-column panels, tall and wide site matrices,
+    rank-deficient columns and a real-valued input; R >= 0 gauge makes the tensors comparable entry by entry"""
+    drv = big_path
+    mpss = [O.random_mps(7, 24, 1), O.random_mps(7, 20, 2, dtype=np.float64).copy()]
+    mpss[1] = [x.astype(np.complex128) for x in mpss[1]]
+    wide = [np.random.default_rng(3).standard_normal((1 if i == 0 else 20, 2, 1 if i == 5 else 20)) + 0j for i in range(6)]
+    wide.append(np.zeros((1, 2, 1), complex))
+    wide = wide[:6]
+    wide[2][:, :, 7] = wide[2][:, :, 3]  # dependent columns
+    for m in mpss + [wide]:
+        for i in range(len(m)):
+            m[i] = m[i] / np.linalg.norm(m[i])
+    for m in (mpss[0], mpss[1], wide):
+        a, b = pack_batch([m], 24)
+        assert drv.left_canonize(a, b).max() == 0
+        g = unpack_batch(a, b)[0]
+        ref = O.left_canonize(O.copy_mps(m))
+        assert O.bonds_of(ref) == O.bonds_of(g)
+        assert abs(O.inner(g, ref) / O.inner(ref, ref) - 1.0) < 1e-12
+        for x, y in zip(ref[:-1], g[:-1]):
+            q = y.reshape(-1, y.shape[2])
+            assert np.abs(q.conj().T @ q - np.eye(q.shape[1])).max() < 1e-12
+        if m is not wide:  # (with dependent columns the QR is not unique)
+            assert max(np.abs(x - y).max() for x, y in zip(ref, g)) < 1e-12

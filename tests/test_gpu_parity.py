@@ -183,12 +183,13 @@ def test_overlap_matches_oracle(drv):
 # ---------------------------------------------------------------------------------------
 def _check_pipeline(drv, tgts, layers, max_bond, D, tol=1e-10, same_convention=True, flags=0, check_svals=True,
                     degenerate=None):
-    """degenerate: None = no instance may report QSP_ST_DEGENERATE (8); True = every instance must."""
+    """degenerate: None = no instance may report QSP_ST_DEGENERATE (8); True = every instance must; "any" = either."""
     a, b = _dev(drv, tgts, D)
     r = drv.seq_prepare(a, b, layers, max_bond=max_bond, flags=flags)
     r = {k: drv.to_host(v) for k, v in r.items()}
     assert (r["status"] & ~8).max() == 0, r["status"]
-    assert ((r["status"] & 8) != 0).all() if degenerate else (r["status"] & 8).max() == 0, r["status"]
+    if degenerate != "any":
+        assert ((r["status"] & 8) != 0).all() if degenerate else (r["status"] & 8).max() == 0, r["status"]
     ev = [i for i in range(layers) if i % 4 == 0 or i == layers - 1]
     for k, tgt in enumerate(tgts):
         dev_layers = [gates_to_layers(r["G"][j, k], r["kind"][j, k]) for j in range(layers)]
@@ -315,7 +316,9 @@ def test_pipeline_edge_cases(drv, name):
 def test_pipeline_six_layers_heisenberg(drv):
     """BASELINE configs[2] shape: Heisenberg L=32 ground state, 6 layers, max_bond_dim=32 (teacher-forced)."""
     z, mps = _load_gold("heisenberg_L32")
-    _check_pipeline(drv, [_prepared(mps)], 6, 32, 32, same_convention=False)
+    # (the SU(2) multiplets of this ground state's Schmidt spectrum are exactly degenerate: QSP_ST_DEGENERATE is reported
+    # wherever a D=2 cut falls inside one)
+    _check_pipeline(drv, [_prepared(mps)], 6, 32, 32, same_convention=False, degenerate="any")
 
 
 def test_pipeline_aklt(drv):
@@ -336,7 +339,7 @@ def test_golden_heisenberg_layer1(drv):
     a, b = _dev(drv, [tg], 64)  # no compression: the working bond doubles once
     r = drv.seq_prepare(a, b, 1, max_bond=0)
     r = {k: drv.to_host(v) for k, v in r.items()}
-    assert r["status"].max() == 0
+    assert (r["status"] & ~8).max() == 0  # (degenerate SU(2) multiplets at some D=2 cuts are reported, bit 8)
     assert abs(abs(r["overlaps"][0, 0]) - 0.5704604532578025) < 1e-11
     assert abs(abs(r["dis"][0, 0]) - abs(z["overlaps"][0])) < 1e-11
     lay = gates_to_layers(r["G"][0, 0], r["kind"][0, 0])
