@@ -27,7 +27,8 @@
 #define QSP_BIG_CK 32   // columns per streamed chunk (rows of W are zero-padded to a multiple of it)
 #define QSP_BIG_LDS 34  // shared row stride of a chunk (complex): 4 k-rows x 32 B hit distinct bank groups
 #define QSP_BIG_LDY 68  // shared row stride of Y = [L | J]
-#define QSP_BIG_NS 3    // TMA ring stages
+#define QSP_BIG_LDJ 36  // shared row stride of J in the update kernel
+#define QSP_BIG_NS 4    // TMA ring stages (two chunks consumed between block barriers, two in flight)
 #define QSP_BIG_NT 256  // threads per CTA of the round and GEMM kernels
 
 // ----------------------------------------------------------------------------------
@@ -166,26 +167,29 @@ struct BigJac {
   double tol2; // rotation threshold on |g|^2 / (alpha beta)
 };
 
-__host__ __device__ inline size_t big_round_smem_bytes() {
-  return (size_t)QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS * sizeof(cplx)  // TMA ring (re-used for the Gram reduction)
-         + (size_t)QSP_BIG_PR * QSP_BIG_LDY * sizeof(cplx)             // Y = [L | J]
-         + 64 * sizeof(double) + QSP_BIG_NS * 16 + 64;
-}
-
 // row r (0..31) of the panel -> row of W, or -1
 __device__ __forceinline__ int big_panel_row(int r, int ra0, int na, int rb0, int nb) {
   if (r < QSP_BIG_RB) return r < na ? ra0 + r : -1;
   return (r - QSP_BIG_RB) < nb ? rb0 + (r - QSP_BIG_RB) : -1;
 }
 
-// flags[inst] |= 1 when a rotation above QSP_JAC_QUAD happened (the sweep has to be repeated)
-__global__ void __launch_bounds__(QSP_BIG_NT) k_big_jacobi_round(const BigJac* __restrict__ jd, int* __restrict__ flags, int round,
-                                                                 int pairs_max) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int inst = blockIdx.x / pairs_max, pi = blockIdx.x - inst * pairs_max;
-  const BigJac J = jd[inst];
+// A round of the block Jacobi = three launches (a CTA owns one block pair = "task" in each of them):
+//   k_big_jac_gram    G = X X^H of the 32-row panel on the tensor cores, panel streamed with TMA; the Gram columns
+//                     can be split over `splits` CTAs (partial Gram matrices, summed in fixed order by the solver)
+//   k_big_jac_solve   32 x 32 problem: convergence test, Cholesky, scalar Jacobi sweep -> unitary J (or "skip")
+//   k_big_jac_update  X <- J X on the tensor cores, columns split over `splits` CTAs
+// Splitting keeps the tensor-core launches many waves deep (no tail) and lets the latency-bound 32 x 32 solves of all
+// pairs run side by side (six CTAs per SM) instead of serialising inside two fat CTAs per SM.
+struct BigTask {
+  int ra0, na, rb0, nbr;  // rows of the two blocks
+  bool live;
+};
+__device__ __forceinline__ BigTask big_task(const BigJac& J, int pi, int round) {
+  BigTask t;
+  t.live = false;
+  t.ra0 = t.na = t.rb0 = t.nbr = 0;
   const int nb = J.nblk;
-  if (nb < 2 || pi >= nb / 2 || round >= nb - 1) return;
+  if (nb < 2 || pi >= nb / 2 || round >= nb - 1) return t;
   int ba, bb;
   if (pi == 0) {
     ba = nb - 1;
@@ -195,118 +199,204 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_jacobi_round(const BigJac* _
     bb = (round + nb - 1 - pi) % (nb - 1);
   }
   if (ba > bb) {
-    const int t = ba;
+    const int x = ba;
     ba = bb;
-    bb = t;
+    bb = x;
   }
-  const int ra0 = ba * QSP_BIG_RB, rb0 = bb * QSP_BIG_RB;
-  const int na = imax(0, imin(QSP_BIG_RB, J.nrows - ra0)), nbr = imax(0, imin(QSP_BIG_RB, J.nrows - rb0));
-  if (na + nbr < 2) return;
+  t.ra0 = ba * QSP_BIG_RB, t.rb0 = bb * QSP_BIG_RB;
+  t.na = imax(0, imin(QSP_BIG_RB, J.nrows - t.ra0)), t.nbr = imax(0, imin(QSP_BIG_RB, J.nrows - t.rb0));
+  t.live = t.na + t.nbr >= 2;
+  return t;
+}
+// chunks [c0, c1) of `nch` handled by split `sp` of `splits`
+__device__ __forceinline__ void big_split_range(int nch, int sp, int splits, int* c0, int* c1) {
+  const int per = (nch + splits - 1) / splits;
+  *c0 = imin(nch, sp * per);
+  *c1 = imin(nch, *c0 + per);
+}
 
-  char* smc = QSP_SMEM_BASE();
-  cplx* ring = (cplx*)smc;
-  cplx* Y = ring + QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS;
-  double* sd = (double*)(Y + QSP_BIG_PR * QSP_BIG_LDY);  // [0..31] diagonal of G, [32] max ratio, [33] rotation flag
-  qsp_mbar* bars = (qsp_mbar*)(sd + 64);
+__host__ __device__ inline size_t big_ring_bytes() { return (size_t)QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS * sizeof(cplx); }
+__host__ __device__ inline size_t big_gram_smem_bytes() { return big_ring_bytes() + QSP_BIG_NS * 16 + 64; }
+__host__ __device__ inline size_t big_solve_smem_bytes() { return (size_t)QSP_BIG_PR * QSP_BIG_LDY * sizeof(cplx) + 64 * sizeof(double) + 64; }
+__host__ __device__ inline size_t big_update_smem_bytes() {
+  return big_ring_bytes() + (size_t)QSP_BIG_PR * QSP_BIG_LDJ * sizeof(cplx) + QSP_BIG_NS * 16 + 64;
+}
 
-  // ---- ring set-up: dead rows stay zero for the whole kernel ------------------------------
-  for (int idx = tid; idx < QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS; idx += QSP_BIG_NT) ring[idx] = cmake(0.0, 0.0);
-  fence_proxy_async();
-  if (tid == 0) {
-    for (int s = 0; s < QSP_BIG_NS; ++s) mbar_init(&bars[s]);
-    fence_mbar_init();
+// TMA ring of 32-row x 32-column chunks of one panel: warp 0 issues one bulk copy per live row, chunks are consumed in
+// issue order (stage = n % NS, parity = (n / NS) & 1)
+struct BigRing {
+  cplx* ring;
+  qsp_mbar* bars;
+  const cplx* W;
+  long ldw;
+  int myrow, nlive, issued, consumed;
+  __device__ __forceinline__ void init(char* smem_ring, qsp_mbar* b, const BigJac& J, const BigTask& t) {
+    ring = (cplx*)smem_ring;
+    bars = b;
+    W = J.W;
+    ldw = J.ldw;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    nlive = t.na + t.nbr;
+    myrow = (warp == 0) ? big_panel_row(lane, t.ra0, t.na, t.rb0, t.nbr) : -1;
+    issued = consumed = 0;
+    // dead rows are zero for the whole kernel (live rows are overwritten by the bulk copies before they are read)
+    if (nlive < QSP_BIG_PR)
+      for (int idx = tid; idx < QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS; idx += blockDim.x) {
+        const int r = (idx / QSP_BIG_LDS) % QSP_BIG_PR;
+        if (big_panel_row(r, t.ra0, t.na, t.rb0, t.nbr) < 0) ring[idx] = cmake(0.0, 0.0);
+      }
+    fence_proxy_async();
+    if (tid == 0) {
+      for (int s = 0; s < QSP_BIG_NS; ++s) mbar_init(&bars[s]);
+      fence_mbar_init();
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  const int nlive = na + nbr;
-  const int myrow = (warp == 0) ? big_panel_row(lane, ra0, na, rb0, nbr) : -1;
-  auto issue = [&](int chunk, int stage) {  // warp 0: one bulk copy per live row of the panel
-    if (warp == 0) {
+  __device__ __forceinline__ void issue(int chunk) {
+    const int stage = issued++ % QSP_BIG_NS;
+    if ((threadIdx.x >> 5) == 0) {
+      const int lane = threadIdx.x & 31;
       if (lane == 0) mbar_expect_tx(&bars[stage], (unsigned)(nlive * QSP_BIG_CK * sizeof(cplx)));
       __syncwarp();
       if (myrow >= 0)
-        tma_load_1d(ring + ((long)stage * QSP_BIG_PR + lane) * QSP_BIG_LDS, J.W + (long)myrow * J.ldw + (long)chunk * QSP_BIG_CK,
+        tma_load_1d(ring + ((long)stage * QSP_BIG_PR + lane) * QSP_BIG_LDS, W + (long)myrow * ldw + (long)chunk * QSP_BIG_CK,
                     (unsigned)(QSP_BIG_CK * sizeof(cplx)), &bars[stage]);
     }
-  };
-  int issued = 0;  // chunks issued so far over both passes (stage = issued % NS, parity = (issued / NS) & 1)
-  int consumed = 0;
+  }
+  __device__ __forceinline__ const cplx* wait_next() {
+    const int stage = consumed % QSP_BIG_NS;
+    mbar_wait(&bars[stage], (consumed / QSP_BIG_NS) & 1);
+    ++consumed;
+    return ring + (long)stage * QSP_BIG_PR * QSP_BIG_LDS;
+  }
+};
 
-  // ---- pass 1: Gram matrix G = X X^H over the Gram columns --------------------------------
-  const int nch1 = J.ndotp / QSP_BIG_CK, nch2 = J.len / QSP_BIG_CK;
+// Gp[task][split][32][32]: partial Gram matrices (full Hermitian storage, row-major)
+__global__ void __launch_bounds__(QSP_BIG_NT) k_big_jac_gram(const BigJac* __restrict__ jd, int round, int pairs_max, int splits,
+                                                             cplx* __restrict__ Gp) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int task = blockIdx.x / splits, sp = blockIdx.x - task * splits;
+  const int inst = task / pairs_max, pi = task - inst * pairs_max;
+  const BigJac J = jd[inst];
+  const BigTask t = big_task(J, pi, round);
+  if (!t.live) return;
+  int c0, c1;
+  big_split_range(J.ndotp / QSP_BIG_CK, sp, splits, &c0, &c1);
+  char* smc = QSP_SMEM_BASE();
+  BigRing R;
+  R.init(smc, (qsp_mbar*)(smc + big_ring_bytes()), J, t);
   ctile acc[10];
 #pragma unroll
-  for (int t = 0; t < 10; ++t) acc[t] = ctile_zero();
+  for (int u = 0; u < 10; ++u) acc[u] = ctile_zero();
   const int fr = lane >> 2, fk = lane & 3;
-  {
-    int next = 0;
-    for (; next < nch1 && next < QSP_BIG_NS - 1; ++next) issue(next, issued++ % QSP_BIG_NS);
-    for (int c = 0; c < nch1; ++c) {
-      if (next < nch1) issue(next++, issued++ % QSP_BIG_NS);
-      const int stage = consumed % QSP_BIG_NS;
-      mbar_wait(&bars[stage], (consumed / QSP_BIG_NS) & 1);
-      ++consumed;
-      const cplx* X = ring + (long)stage * QSP_BIG_PR * QSP_BIG_LDS;
-      // warp w takes k-step w of the chunk (columns 4w .. 4w+3): four row-tile fragments feed all ten tiles
+  int next = c0;
+  for (; next < c1 && next < c0 + 2; ++next) R.issue(next);
+  for (int c = c0; c < c1; c += 2) {
+    for (int u = 0; u < 2 && next < c1; ++u) R.issue(next++);
+    for (int u = 0; u < 2 && c + u < c1; ++u) {
+      const cplx* X = R.wait_next();
+      // warp w takes k-step w of the chunk (columns 4w .. 4w+3): four row-tile fragments feed all ten tiles; the four
+      // real DMMAs of a complex tile are issued tile-interleaved so that no DMMA waits for its predecessor
       cplx f[4];
 #pragma unroll
       for (int ti = 0; ti < 4; ++ti) f[ti] = X[(ti * 8 + fr) * QSP_BIG_LDS + warp * 4 + fk];
-      int t = 0;
+      int q = 0;
 #pragma unroll
       for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
-        for (int tj = ti; tj < 4; ++tj) cdmma_bh(acc[t++], f[ti].x, f[ti].y, f[tj].x, f[tj].y);
-      __syncthreads();
-    }
-  }
-  // ---- reduce the eight partial Gram matrices (deterministic tree through the idle ring) ---
-  {
-    double* part = (double*)ring;  // [warp][tile][4][32 lanes]
-    for (int half = 4; half >= 1; half >>= 1) {
-      if (warp >= half && warp < 2 * half) {
-        double* p = part + (long)(warp - half) * 10 * 4 * 32;
-#pragma unroll
-        for (int t = 0; t < 10; ++t) {
-          p[(t * 4 + 0) * 32 + lane] = acc[t].r0;
-          p[(t * 4 + 1) * 32 + lane] = acc[t].r1;
-          p[(t * 4 + 2) * 32 + lane] = acc[t].i0;
-          p[(t * 4 + 3) * 32 + lane] = acc[t].i1;
-        }
-      }
-      __syncthreads();
-      if (warp < half) {
-        const double* p = part + (long)warp * 10 * 4 * 32;
-#pragma unroll
-        for (int t = 0; t < 10; ++t) {
-          acc[t].r0 += p[(t * 4 + 0) * 32 + lane];
-          acc[t].r1 += p[(t * 4 + 1) * 32 + lane];
-          acc[t].i0 += p[(t * 4 + 2) * 32 + lane];
-          acc[t].i1 += p[(t * 4 + 3) * 32 + lane];
-        }
-      }
-      __syncthreads();
-    }
-    if (warp == 0) {
-      int t = 0;
+        for (int tj = ti; tj < 4; ++tj, ++q) dmma_8x8x4(acc[q].r0, acc[q].r1, f[ti].x, f[tj].x);
+      q = 0;
 #pragma unroll
       for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
-        for (int tj = ti; tj < 4; ++tj) {
-          const int r = ti * 8 + fr, c = tj * 8 + 2 * fk;
-          const cplx v0 = cmake(acc[t].r0, acc[t].i0), v1 = cmake(acc[t].r1, acc[t].i1);
-          Y[r * QSP_BIG_LDY + c] = v0;
-          Y[r * QSP_BIG_LDY + c + 1] = v1;
-          if (tj > ti) {
-            Y[c * QSP_BIG_LDY + r] = cconj(v0);
-            Y[(c + 1) * QSP_BIG_LDY + r] = cconj(v1);
-          }
-          ++t;
-        }
+        for (int tj = ti; tj < 4; ++tj, ++q) dmma_8x8x4(acc[q].i0, acc[q].i1, f[ti].y, f[tj].x);
+      q = 0;
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < 4; ++tj, ++q) dmma_8x8x4(acc[q].r0, acc[q].r1, f[ti].y, f[tj].y);
+      q = 0;
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < 4; ++tj, ++q) dmma_8x8x4(acc[q].i0, acc[q].i1, -f[ti].x, f[tj].y);
     }
     __syncthreads();
-    // the ring is the zero-padded TMA target again
-    for (int idx = tid; idx < QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS; idx += QSP_BIG_NT) ring[idx] = cmake(0.0, 0.0);
-    fence_proxy_async();
   }
+  // ---- reduce the eight partial Gram matrices (deterministic tree through the idle ring) ---
+  double* part = (double*)R.ring;  // [warp][tile][4][32 lanes]
+  for (int half = 4; half >= 1; half >>= 1) {
+    if (warp >= half && warp < 2 * half) {
+      double* p = part + (long)(warp - half) * 10 * 4 * 32;
+#pragma unroll
+      for (int u = 0; u < 10; ++u) {
+        p[(u * 4 + 0) * 32 + lane] = acc[u].r0;
+        p[(u * 4 + 1) * 32 + lane] = acc[u].r1;
+        p[(u * 4 + 2) * 32 + lane] = acc[u].i0;
+        p[(u * 4 + 3) * 32 + lane] = acc[u].i1;
+      }
+    }
+    __syncthreads();
+    if (warp < half) {
+      const double* p = part + (long)warp * 10 * 4 * 32;
+#pragma unroll
+      for (int u = 0; u < 10; ++u) {
+        acc[u].r0 += p[(u * 4 + 0) * 32 + lane];
+        acc[u].r1 += p[(u * 4 + 1) * 32 + lane];
+        acc[u].i0 += p[(u * 4 + 2) * 32 + lane];
+        acc[u].i1 += p[(u * 4 + 3) * 32 + lane];
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    cplx* G = Gp + ((long)task * splits + sp) * QSP_BIG_PR * QSP_BIG_PR;
+    int q = 0;
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = ti; tj < 4; ++tj, ++q) {
+        const int r = ti * 8 + fr, c = tj * 8 + 2 * fk;
+        const cplx v0 = cmake(acc[q].r0, acc[q].i0), v1 = cmake(acc[q].r1, acc[q].i1);
+        G[r * QSP_BIG_PR + c] = v0;
+        G[r * QSP_BIG_PR + c + 1] = v1;
+        if (tj > ti) {
+          G[c * QSP_BIG_PR + r] = cconj(v0);
+          G[(c + 1) * QSP_BIG_PR + r] = cconj(v1);
+        }
+      }
+  }
+}
+
+// flags[inst] |= 1 when a rotation above QSP_JAC_QUAD happened (the sweep has to be repeated).
+// Jg[task][32][32] receives the unitary of the pair, skip[task] = 1 when the pair needed no rotation.
+__global__ void __launch_bounds__(QSP_BIG_NT, 4) k_big_jac_solve(const BigJac* __restrict__ jd, int* __restrict__ flags, int round, int pairs_max,
+                                                              int splits, const cplx* __restrict__ Gp, cplx* __restrict__ Jg,
+                                                              int* __restrict__ skip) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int task = blockIdx.x;
+  const int inst = task / pairs_max, pi = task - inst * pairs_max;
+  const BigJac J = jd[inst];
+  const BigTask t = big_task(J, pi, round);
+  if (!t.live) {
+    if (tid == 0) skip[task] = 1;
+    return;
+  }
+  char* smc = QSP_SMEM_BASE();
+  cplx* Y = (cplx*)smc;
+  double* sd = (double*)(Y + QSP_BIG_PR * QSP_BIG_LDY);  // [0..31] diagonal of G, [32] max ratio, [33] rotation flag
+  {  // G = sum of the column-split partials, in fixed order
+    int c0, c1;
+    for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT) {
+      cplx v = cmake(0.0, 0.0);
+      for (int sp = 0; sp < splits; ++sp) {
+        big_split_range(J.ndotp / QSP_BIG_CK, sp, splits, &c0, &c1);
+        if (c1 > c0) v = cadd(v, Gp[((long)task * splits + sp) * QSP_BIG_PR * QSP_BIG_PR + idx]);
+      }
+      Y[(idx / QSP_BIG_PR) * QSP_BIG_LDY + (idx % QSP_BIG_PR)] = v;
+    }
+  }
+  __syncthreads();
   // ---- convergence of this block pair: max |g_pq|^2 / (g_pp g_qq) ---------------------------
   if (warp == 0) {
     const double dp = Y[lane * QSP_BIG_LDY + lane].x;
@@ -324,55 +414,77 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_jacobi_round(const BigJac* _
   }
   __syncthreads();
   const double maxratio = sd[32];
-  if (!(maxratio > J.tol2)) return;  // nothing to rotate in this pair
-  if (tid == 0 && maxratio > QSP_JAC_QUAD * QSP_JAC_QUAD) flags[inst] = 1;
+  if (!(maxratio > J.tol2)) {  // nothing to rotate in this pair
+    if (tid == 0) skip[task] = 1;
+    return;
+  }
+  if (tid == 0) {
+    skip[task] = 0;
+    if (maxratio > QSP_JAC_QUAD * QSP_JAC_QUAD) flags[inst] = 1;
+  }
 
-  // ---- Cholesky G = L L^H in place (lower triangle); dependent rows give zero columns -------
+  // ---- Cholesky G = L L^H: L is built in the right half of Y (one barrier per column: the trailing update reads the
+  // UNSCALED column j of G and divides by the pivot on the fly); dependent rows give zero columns -------------------
+  cplx* Lh = Y + QSP_BIG_PR;  // L[i][j] at Lh[i * LDY + j]
   for (int j = 0; j < QSP_BIG_PR; ++j) {
-    __syncthreads();  // trailing update of column j - 1 done
     const double piv = Y[j * QSP_BIG_LDY + j].x;
     const bool ok = piv > 4e-15 * sd[j] && piv > 0.0;
-    const double inv = ok ? qsp_rsqrt(piv) : 0.0;
-    __syncthreads();  // everybody has read the pivot
-    if (tid < QSP_BIG_PR - j) {
-      const int i = j + tid;
-      cplx v = Y[i * QSP_BIG_LDY + j];
-      Y[i * QSP_BIG_LDY + j] = (i == j) ? cmake(ok ? piv * inv : 0.0, 0.0) : cscale(v, inv);
+    double inv = 0.0;  // 1 / sqrt(pivot): one lane per warp computes it (the FP64 pipe is shared with three other CTAs)
+    if (lane == 0 && ok) inv = qsp_rsqrt(piv);
+    inv = __shfl_sync(QSP_FULL_MASK, inv, 0);
+    const double ipiv = inv * inv;
+    if (tid < QSP_BIG_PR) {  // column j of L (rows >= j), zeros above the diagonal
+      const int i = tid;
+      cplx v = cmake(0.0, 0.0);
+      if (i == j) v = cmake(ok ? piv * inv : 0.0, 0.0);
+      else if (i > j) v = cscale(Y[i * QSP_BIG_LDY + j], inv);
+      Lh[i * QSP_BIG_LDY + j] = v;
     }
-    __syncthreads();
     if (ok) {
-      const int rem = QSP_BIG_PR - 1 - j;
-      for (int idx = tid; idx < rem * rem; idx += QSP_BIG_NT) {
-        const int i = j + 1 + idx / rem, k = j + 1 + idx % rem;
-        if (k <= i) {
-          const cplx li = Y[i * QSP_BIG_LDY + j], lk = Y[k * QSP_BIG_LDY + j];
+      // trailing update of the lower triangle: thread (i, k-lane) pairs, rows i = j+1.., eight k per row and pass
+      const int i = j + 1 + (tid >> 3);
+      if (i < QSP_BIG_PR) {
+        const cplx gi = Y[i * QSP_BIG_LDY + j];
+        for (int k = j + 1 + (tid & 7); k <= i; k += 8) {
+          const cplx gk = Y[k * QSP_BIG_LDY + j];
           cplx v = Y[i * QSP_BIG_LDY + k];
-          // v -= li * conj(lk)
-          v.x -= li.x * lk.x + li.y * lk.y;
-          v.y -= li.y * lk.x - li.x * lk.y;
+          // v -= gi * conj(gk) / piv
+          v.x -= (gi.x * gk.x + gi.y * gk.y) * ipiv;
+          v.y -= (gi.y * gk.x - gi.x * gk.y) * ipiv;
           Y[i * QSP_BIG_LDY + k] = v;
         }
       }
     }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT) {  // Y <- [L | I]
+    const int i = idx / QSP_BIG_PR, k = idx - i * QSP_BIG_PR;
+    Y[i * QSP_BIG_LDY + k] = Lh[i * QSP_BIG_LDY + k];
   }
   __syncthreads();
   for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT) {
     const int i = idx / QSP_BIG_PR, k = idx - i * QSP_BIG_PR;
-    if (k > i) Y[i * QSP_BIG_LDY + k] = cmake(0.0, 0.0);
-    Y[i * QSP_BIG_LDY + QSP_BIG_PR + k] = cmake(i == k ? 1.0 : 0.0, 0.0);
+    Lh[i * QSP_BIG_LDY + k] = cmake(i == k ? 1.0 : 0.0, 0.0);
   }
   __syncthreads();
 
-  // ---- scalar Jacobi on the rows of L, rotations accumulated in J (right half of Y) ----------
+  // ---- scalar Jacobi on the rows of L, rotations accumulated in J (right half of Y).  The pairs inside a 16-row block
+  // are visited in round 0 of a sweep only (every block is paired in every round); later rounds rotate the 16 x 16 pairs
+  // between the two blocks. ---------------------------------------------------------------------------------------
   {
     const int team = tid >> 4, tl = tid & 15;  // 16 pairs x 16 lanes
     volatile double* rotflag = sd + 33;
+    const bool bip = round > 0;
+    const int nr = bip ? QSP_BIG_RB : QSP_BIG_PR - 1;
     for (int sw = 0; sw < J.inner; ++sw) {
       if (tid == 0) *rotflag = 0.0;
       __syncthreads();
-      for (int r = 0; r < QSP_BIG_PR - 1; ++r) {
+      for (int r = 0; r < nr; ++r) {
         int a, b;
-        if (team == 0) {
+        if (bip) {
+          a = team;
+          b = QSP_BIG_RB + ((team + r) & (QSP_BIG_RB - 1));
+        } else if (team == 0) {
           a = QSP_BIG_PR - 1;
           b = r;
         } else {
@@ -403,9 +515,13 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_jacobi_round(const BigJac* _
           gy += shfl_xor_d(gy, o);
         }
         const double g2 = gx * gx + gy * gy, ab = al * be;
-        if (ab > 1e-280 && g2 > J.tol2 * ab) {
-          double cs, sx, sy;
-          jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
+        const bool rot = ab > 1e-280 && g2 > J.tol2 * ab;
+        double cs = 1.0, sx = 0.0, sy = 0.0;  // the team leader computes the rotation, the team gets it by shuffle
+        if (rot && tl == 0) jacobi_rotation(al, be, gx, gy, g2, cs, sx, sy);
+        cs = __shfl_sync(QSP_FULL_MASK, cs, 0, 16);
+        sx = __shfl_sync(QSP_FULL_MASK, sx, 0, 16);
+        sy = __shfl_sync(QSP_FULL_MASK, sy, 0, 16);
+        if (rot) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             cplx xn, yn;
@@ -425,46 +541,76 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_jacobi_round(const BigJac* _
     }
   }
   __syncthreads();
+  cplx* Jo = Jg + (long)task * QSP_BIG_PR * QSP_BIG_PR;
+  for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT)
+    Jo[idx] = Y[(idx / QSP_BIG_PR) * QSP_BIG_LDY + QSP_BIG_PR + (idx % QSP_BIG_PR)];
+}
 
-  // ---- pass 2: X <- J X on all columns, J fragments register resident ------------------------
-  {
-    const int rt0 = (warp >> 2) * 2, ct = warp & 3;
-    double jr[2][8], ji[2][8];
+// X <- J X on the columns of split `sp`, J fragments register resident
+__global__ void __launch_bounds__(QSP_BIG_NT) k_big_jac_update(const BigJac* __restrict__ jd, int round, int pairs_max, int splits,
+                                                               const cplx* __restrict__ Jg, const int* __restrict__ skip) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int task = blockIdx.x / splits, sp = blockIdx.x - task * splits;
+  if (skip[task]) return;
+  const int inst = task / pairs_max, pi = task - inst * pairs_max;
+  const BigJac J = jd[inst];
+  const BigTask t = big_task(J, pi, round);
+  if (!t.live) return;
+  int c0, c1;
+  big_split_range(J.len / QSP_BIG_CK, sp, splits, &c0, &c1);
+  if (c1 <= c0) return;
+  char* smc = QSP_SMEM_BASE();
+  cplx* Js = (cplx*)(smc + big_ring_bytes());
+  BigRing R;
+  R.init(smc, (qsp_mbar*)(Js + QSP_BIG_PR * QSP_BIG_LDJ), J, t);
+  int next = c0;
+  for (; next < c1 && next < c0 + 2; ++next) R.issue(next);
+  const cplx* Ji = Jg + (long)task * QSP_BIG_PR * QSP_BIG_PR;
+  for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT)
+    Js[(idx / QSP_BIG_PR) * QSP_BIG_LDJ + (idx % QSP_BIG_PR)] = Ji[idx];
+  __syncthreads();
+  const int fr = lane >> 2, fk = lane & 3;
+  const int rt0 = (warp >> 2) * 2, ct = warp & 3;
+  double jr[2][8], ji[2][8];
 #pragma unroll
-    for (int t = 0; t < 2; ++t)
+  for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const cplx v = Y[((rt0 + t) * 8 + fr) * QSP_BIG_LDY + QSP_BIG_PR + ks * 4 + fk];
-        jr[t][ks] = v.x;
-        ji[t][ks] = v.y;
-      }
-    int orow[2];
+    for (int ks = 0; ks < 8; ++ks) {
+      const cplx v = Js[((rt0 + u) * 8 + fr) * QSP_BIG_LDJ + ks * 4 + fk];
+      jr[u][ks] = v.x;
+      ji[u][ks] = v.y;
+    }
+  int orow[2];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) orow[t] = big_panel_row((rt0 + t) * 8 + fr, ra0, na, rb0, nbr);
-    int next = 0;
-    for (; next < nch2 && next < QSP_BIG_NS - 1; ++next) issue(next, issued++ % QSP_BIG_NS);
-    for (int c = 0; c < nch2; ++c) {
-      if (next < nch2) issue(next++, issued++ % QSP_BIG_NS);
-      const int stage = consumed % QSP_BIG_NS;
-      mbar_wait(&bars[stage], (consumed / QSP_BIG_NS) & 1);
-      ++consumed;
-      const cplx* X = ring + (long)stage * QSP_BIG_PR * QSP_BIG_LDS;
+  for (int u = 0; u < 2; ++u) orow[u] = big_panel_row((rt0 + u) * 8 + fr, t.ra0, t.na, t.rb0, t.nbr);
+  int cdone = c0;
+  for (int c = c0; c < c1; c += 2) {
+    for (int u = 0; u < 2 && next < c1; ++u) R.issue(next++);
+    for (int u = 0; u < 2 && c + u < c1; ++u, ++cdone) {
+      const cplx* X = R.wait_next();
       ctile o[2] = {ctile_zero(), ctile_zero()};
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
         const cplx bq = X[(ks * 4 + fk) * QSP_BIG_LDS + ct * 8 + fr];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) cdmma(o[t], jr[t][ks], ji[t][ks], bq.x, bq.y);
+        // (re, im) of both row tiles interleaved: four independent accumulators per k-step
+        dmma_8x8x4(o[0].r0, o[0].r1, jr[0][ks], bq.x);
+        dmma_8x8x4(o[1].r0, o[1].r1, jr[1][ks], bq.x);
+        dmma_8x8x4(o[0].i0, o[0].i1, jr[0][ks], bq.y);
+        dmma_8x8x4(o[1].i0, o[1].i1, jr[1][ks], bq.y);
+        dmma_8x8x4(o[0].r0, o[0].r1, -ji[0][ks], bq.y);
+        dmma_8x8x4(o[1].r0, o[1].r1, -ji[1][ks], bq.y);
+        dmma_8x8x4(o[0].i0, o[0].i1, ji[0][ks], bq.x);
+        dmma_8x8x4(o[1].i0, o[1].i1, ji[1][ks], bq.x);
       }
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
-        if (orow[t] >= 0) {
-          cplx* dst = J.W + (long)orow[t] * J.ldw + (long)c * QSP_BIG_CK + ct * 8 + 2 * fk;
-          dst[0] = cmake(o[t].r0, o[t].i0);
-          dst[1] = cmake(o[t].r1, o[t].i1);
+      for (int u2 = 0; u2 < 2; ++u2)
+        if (orow[u2] >= 0) {
+          cplx* dst = J.W + (long)orow[u2] * J.ldw + (long)cdone * QSP_BIG_CK + ct * 8 + 2 * fk;
+          dst[0] = cmake(o[u2].r0, o[u2].i0);
+          dst[1] = cmake(o[u2].r1, o[u2].i1);
         }
-      __syncthreads();
     }
+    __syncthreads();
   }
 }
 

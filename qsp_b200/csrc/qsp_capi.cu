@@ -315,9 +315,10 @@ extern "C" void qsp_debug_flags(int flags) {
 // matrices beyond 128 x 128 no longer fit the register + shared memory of one SM
 static bool rcompress_is_big(int DinL, int DoutL) { return g_force_big || imax(DinL / 2, DoutL) > 64; }
 struct BigRCLayout {
-  size_t off_S, off_jd, off_g1, off_g2, off_gU, off_flags, off_any, off_sweeps, off_work, total;
+  size_t off_S, off_jd, off_g1, off_g2, off_gU, off_flags, off_any, off_sweeps, off_jw, off_work, total;
   long stride;
 };
+static size_t big_jacobi_scratch_bytes(int B, int nrows_max, int len_max);
 static BigRCLayout big_rc_layout(int B, int DinL, int DoutL) {
   BigRCLayout l;
   size_t o = 0;
@@ -329,6 +330,7 @@ static BigRCLayout big_rc_layout(int B, int DinL, int DoutL) {
   l.off_flags = o, o += align_up((size_t)B * sizeof(int));
   l.off_any = o, o += 256;
   l.off_sweeps = o, o += align_up((size_t)B * sizeof(int));
+  l.off_jw = o, o += big_jacobi_scratch_bytes(B, 2 * DoutL, DinL + 2 * DoutL + 64);
   l.off_work = o;
   l.stride = rcompress_work_elems(DinL, DoutL);
   l.total = o + align_up((size_t)B * l.stride * sizeof(cplx));
@@ -342,18 +344,36 @@ static int launch_big_gemm(const BigGemm* gd, int ndesc, int m_max, int n_max, q
   ++g_launches;
   return QSP_OK;
 }
-// block Jacobi SVD of the B matrices described by jd (device); nrows_max bounds every instance's row count
-static int big_jacobi_run(BigJac* jd, int B, int nrows_max, int* flags, int* any, int* sweeps, qsp_stream_t st) {
+// block Jacobi SVD of the B matrices described by jd (device); nrows_max / len_max bound every instance's extents.
+// jw: scratch of big_jacobi_scratch_bytes(B, nrows_max, len_max) (partial Gram matrices, pair unitaries, skip flags)
+static int big_jacobi_splits(int len_max) { return imax(1, imin(4, len_max / (4 * QSP_BIG_CK))); }
+static size_t big_jacobi_scratch_bytes(int B, int nrows_max, int len_max) {
+  const int nblk = ((nrows_max + QSP_BIG_RB - 1) / QSP_BIG_RB + 1) & ~1;
+  const size_t tasks = (size_t)B * (nblk / 2), tile = (size_t)QSP_BIG_PR * QSP_BIG_PR * sizeof(cplx);
+  return align_up(tasks * big_jacobi_splits(len_max) * tile) + align_up(tasks * tile) + align_up(tasks * sizeof(int));
+}
+static int big_jacobi_run(BigJac* jd, int B, int nrows_max, int len_max, int* flags, int* any, int* sweeps, void* jw, qsp_stream_t st) {
   if (nrows_max < 2) return QSP_OK;
   const int nblk = ((nrows_max + QSP_BIG_RB - 1) / QSP_BIG_RB + 1) & ~1;
-  const int pairs = nblk / 2, rounds = nblk - 1;
-  QSP_PREP_KERNEL(k_big_jacobi_round, big_round_smem_bytes());
+  const int pairs = nblk / 2, rounds = nblk - 1, splits = big_jacobi_splits(len_max);
+  const int gsplits = imax(1, splits / 2);  // the Gram launch pays a cross-warp reduction per CTA: split it less
+  const size_t tasks = (size_t)B * pairs, tile = (size_t)QSP_BIG_PR * QSP_BIG_PR * sizeof(cplx);
+  cplx* Gp = (cplx*)jw;
+  cplx* Jg = (cplx*)((char*)jw + align_up(tasks * splits * tile));
+  int* skip = (int*)((char*)Jg + align_up(tasks * tile));
+  QSP_PREP_KERNEL(k_big_jac_gram, big_gram_smem_bytes());
+  QSP_PREP_KERNEL(k_big_jac_solve, big_solve_smem_bytes());
+  QSP_PREP_KERNEL(k_big_jac_update, big_update_smem_bytes());
   dev_zero(flags, (size_t)B * sizeof(int), st);
   for (int sw = 0; sw < QSP_BIG_MAX_SWEEPS; ++sw) {
     dev_zero(any, sizeof(int), st);
     for (int r = 0; r < rounds; ++r) {
-      QSP_LAUNCH(k_big_jacobi_round, B * pairs, QSP_BIG_NT, big_round_smem_bytes(), st, (const BigJac*)jd, flags, r, pairs);
-      ++g_launches;
+      QSP_LAUNCH(k_big_jac_gram, (int)tasks * gsplits, QSP_BIG_NT, big_gram_smem_bytes(), st, (const BigJac*)jd, r, pairs, gsplits, Gp);
+      QSP_LAUNCH(k_big_jac_solve, (int)tasks, QSP_BIG_NT, big_solve_smem_bytes(), st, (const BigJac*)jd, flags, r, pairs, gsplits,
+                 (const cplx*)Gp, Jg, skip);
+      QSP_LAUNCH(k_big_jac_update, (int)tasks * splits, QSP_BIG_NT, big_update_smem_bytes(), st, (const BigJac*)jd, r, pairs, splits,
+                 (const cplx*)Jg, (const int*)skip);
+      g_launches += 3;
     }
     QSP_LAUNCH(k_big_sweep_end, (B + 127) / 128, 128, 0, st, jd, flags, any, sweeps, B);
     ++g_launches;
@@ -415,7 +435,8 @@ static int big_right_compress(const RCompressArgs& a0, void* work, size_t work_b
     const int nrows_max = imin(b_max, c_max);
     QSP_LAUNCH(k_big_rc_jprep, B * parts, 256, 0, st, a, (const BigRCState*)S, jd, parts);
     ++g_launches;
-    if ((rc = big_jacobi_run(jd, B, nrows_max, flags, any, sweeps, st))) return rc;
+    const int len_max = big_r32(imax(b_max, c_max)) + (b_max > c_max ? big_r32(c_max) : 0);
+    if ((rc = big_jacobi_run(jd, B, nrows_max, len_max, flags, any, sweeps, w + lay.off_jw, st))) return rc;
     const size_t rsm = big_rank_smem_bytes(nrows_max);
     QSP_PREP_KERNEL(k_big_rc_rank, rsm);
     QSP_LAUNCH(k_big_rc_rank, B, 256, rsm, st, a, S, (const BigJac*)jd, i, gU);

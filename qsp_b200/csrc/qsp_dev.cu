@@ -185,13 +185,17 @@ extern "C" int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int 
 
 // Block-Jacobi SVD of the large-bond path on its own (tests, micro-benchmarks, ncu): the rows of the B matrices
 // W[B][nrows][ldw] are orthogonalised in place (ldw, ndotp multiples of 32, zero padded); sweeps[B] receives the sweep
-// counts, ok[B] 1 on convergence.  work: B * 64 + 1024 bytes of device memory.
+// counts, ok[B] 1 on convergence.  work: qsp_big_jacobi_work_bytes(nrows, ldw, B) bytes of device memory.
+extern "C" size_t qsp_big_jacobi_work_bytes(int nrows, int ldw, int B) {
+  return align_up((size_t)B * sizeof(BigJac)) + align_up((size_t)(B + 1) * sizeof(int)) + big_jacobi_scratch_bytes(B, nrows, ldw);
+}
 extern "C" int qsp_big_jacobi(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int* sweeps, int* ok, void* work, void* stream) {
   if (!W || !sweeps || !ok || !work || B <= 0 || nrows < 1 || ldw % QSP_BIG_CK || ndotp % QSP_BIG_CK || ndotp > ldw) return QSP_ERR_ARG;
   qsp_stream_t st = (qsp_stream_t)stream;
   BigJac* jd = (BigJac*)work;
   int* flags = (int*)((char*)work + align_up((size_t)B * sizeof(BigJac)));
   int* any = flags + B;
+  void* jw = (char*)work + align_up((size_t)B * sizeof(BigJac)) + align_up((size_t)(B + 1) * sizeof(int));
   std::vector<BigJac> h(B);
   const double tol = 4e-16 * sqrt((double)ndotp);
   for (int b = 0; b < B; ++b) {
@@ -209,7 +213,7 @@ extern "C" int qsp_big_jacobi(qsp_c128* W, int nrows, int ndotp, int ldw, int B,
   cudaStreamSynchronize(st);
 #endif
   dev_zero(sweeps, (size_t)B * sizeof(int), st);
-  int rc = big_jacobi_run(jd, B, nrows, flags, any, sweeps, st);
+  int rc = big_jacobi_run(jd, B, nrows, ldw, flags, any, sweeps, jw, st);
   if (rc) return rc;
 #ifdef QSP_EMU
   for (int b = 0; b < B; ++b) ok[b] = jd[b].nblk == 0;

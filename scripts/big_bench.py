@@ -15,7 +15,7 @@ s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 g = torch.Generator(device=dev); g.manual_seed(1)
 W0 = torch.complex(torch.randn((B, n, n), generator=g, device=dev, dtype=torch.float64),
                    torch.randn((B, n, n), generator=g, device=dev, dtype=torch.float64))
-work = torch.zeros(B * 128 + 4096, dtype=torch.uint8, device=dev)
+work = torch.zeros(max(lib.qsp_big_jacobi_work_bytes(n, n, B), B * 128 + 4096), dtype=torch.uint8, device=dev)
 sw = torch.zeros(B, dtype=torch.int32, device=dev); ok = torch.zeros(B, dtype=torch.int32, device=dev)
 for rep in range(3):
     W = W0.clone()

@@ -381,7 +381,7 @@ def test_big_block_jacobi(drv, nrows, ndot, extra):
             W[b, :, ndot:ndot + nrows] = np.eye(nrows)
     W0 = W.copy()
     sw, ok = np.zeros(B, np.int32), np.zeros(B, np.int32)
-    work = np.zeros(B * 64 + 1024, np.uint8)
+    work = np.zeros(drv.lib.qsp_big_jacobi_work_bytes(nrows, ldw, B), np.uint8)
     drv.lib.qsp_big_jacobi(drv.p(W), nrows, ndot, ldw, B, drv.p(sw), drv.p(ok), drv.p(work), None)
     assert ok.all() and sw.max() <= 20, (ok, sw)
     for b in range(B):

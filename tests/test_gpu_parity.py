@@ -59,8 +59,8 @@ def test_left_canonize_matches_oracle(drv, L, chi):
     for m, g in zip(mpss, got):
         ref = O.left_canonize(O.copy_mps(m))
         assert O.bonds_of(ref) == O.bonds_of(g)
-        for x, y in zip(ref, g):
-            assert np.abs(x - y).max() < 1e-12
+        for x, y in zip(ref, g):  # (512 x 256 site matrices: blocked Householder vs LAPACK, entry by entry)
+            assert np.abs(x - y).max() < (1e-12 if chi <= 64 else 5e-12)
 
 
 @pytest.mark.parametrize("L,chi,max_bond", [(8, 8, 4), (12, 16, 0), (16, 64, 32), (10, 32, 2), (30, 128, 64)])
