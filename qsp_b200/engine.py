@@ -4,6 +4,7 @@ is a call into libqsp_b200.so (include/qsp_b200.h).
 Layout: a batch of B MPS of L sites is `mps[B, L, D, 2, D]` complex128 with the
 live bond extents in `bonds[B, L+1]` int32; element (l, p, r) of a site is mps[b, i, l, p, r].
 """
+import contextlib
 import ctypes
 
 import numpy as np
@@ -66,6 +67,7 @@ class Engine:
         self.device = torch.device(device)
         self._work = None
         self._work_key = None
+        self._side = None  # two side streams (+ workspaces) for overlapping the chunks of one seq_prepare call
 
     # ---- memory ---------------------------------------------------------------------------
     def _workspace(self, nbytes):
@@ -86,7 +88,7 @@ class Engine:
         """Largest chunk of instances whose workspace fits the memory budget."""
         if budget_bytes is None:
             free, _ = torch.cuda.mem_get_info(self.device)
-            budget_bytes = int(free * 0.6)
+            budget_bytes = int(free * 0.35)  # (two chunks are in flight at a time, see seq_prepare)
         c = B
         while c > 1 and self.seq_workspace_bytes(c, L, D, layers, max_bond, flags) > budget_bytes:
             c = (c + 1) // 2
@@ -183,7 +185,7 @@ class Engine:
 
     # ---- the layer loop ---------------------------------------------------------------------
     def seq_prepare(self, target, bonds, layers, max_bond=0, cutoff=CUTOFF, overlaps_gap=4, second_pass=False,
-                    encoded=True, want_final=False, chunk=None):
+                    encoded=True, want_final=False, chunk=None, overlap_chunks=True):
         """sequential_unitary_circuit (sequential.py:42-85) for target[B,L,D,2,D] (device)."""
         if target.dtype != torch.complex128 or bonds.dtype != torch.int32:
             raise TypeError("target must be complex128 and bonds int32")
@@ -202,28 +204,57 @@ class Engine:
         finb = torch.empty_like(bonds) if want_final else None
         if chunk is None:
             chunk = self.pick_chunk(B, L, D, layers, max_bond, flags)
-        stream = _runtime.current_stream_ptr()
-        for b0 in range(0, B, chunk):
+        starts = list(range(0, B, chunk))
+        # Chunks alternate between two streams (each with its own workspace): every sweep kernel is a grid of persistent
+        # one-per-SM CTAs pulling instances from a queue, so its last instances leave SMs idle -- the next chunk's kernels
+        # (other stream) fill them.  A single chunk runs on the caller's stream.
+        cur = torch.cuda.current_stream(dev)
+        two = len(starts) > 1 and overlap_chunks
+        if two:
+            if self._side is None:
+                self._side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+                self._side_work = [None, None]
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)
+            for s_ in self._side:
+                s_.wait_event(ev0)
+        for ci, b0 in enumerate(starts):
             b1 = min(B, b0 + chunk)
             n = b1 - b0
             nb = self.seq_workspace_bytes(n, L, D, layers, max_bond, flags)
-            work = self._workspace(nb)
             whole = n == B
-            c_ov = ov if whole else torch.empty((layers, n), dtype=torch.complex128, device=dev)
-            c_dis = dis if whole else torch.empty((layers, n), dtype=torch.complex128, device=dev)
-            c_G = G if whole else torch.empty((layers, n, L, 4, 4), dtype=torch.complex128, device=dev)
-            c_kind = kind if whole else torch.empty((layers, n, L), dtype=torch.int32, device=dev)
-            c_sv = sv if whole else torch.empty((layers, n, max(L - 1, 1), 2), dtype=torch.float64, device=dev)
-            self.lib.qsp_seq_prepare(_p(target[b0:b1]), _p(bonds[b0:b1]), n, L, D, layers, max_bond, cutoff,
-                                     overlaps_gap, flags, _p(c_ov), _p(c_dis), _p(c_G), _p(c_kind), _p(c_sv),
-                                     _p(fin[b0:b1]) if want_final else None,
-                                     _p(finb[b0:b1]) if want_final else None, _p(status[b0:b1]), _p(work), nb, stream)
-            if not whole:
-                ov[:, b0:b1] = c_ov
-                dis[:, b0:b1] = c_dis
-                G[:, b0:b1] = c_G
-                kind[:, b0:b1] = c_kind
-                sv[:, b0:b1] = c_sv
+            if two:
+                k = ci % 2
+                if self._side_work[k] is None or self._side_work[k].numel() < nb:
+                    self._side_work[k] = None
+                    self._side_work[k] = torch.empty(int(nb), dtype=torch.uint8, device=dev)
+                work, ctx = self._side_work[k], torch.cuda.stream(self._side[k])
+            else:
+                work, ctx = self._workspace(nb), contextlib.nullcontext()
+            with ctx:
+                stream = _runtime.current_stream_ptr()
+                c_ov = ov if whole else torch.empty((layers, n), dtype=torch.complex128, device=dev)
+                c_dis = dis if whole else torch.empty((layers, n), dtype=torch.complex128, device=dev)
+                c_G = G if whole else torch.empty((layers, n, L, 4, 4), dtype=torch.complex128, device=dev)
+                c_kind = kind if whole else torch.empty((layers, n, L), dtype=torch.int32, device=dev)
+                c_sv = sv if whole else torch.empty((layers, n, max(L - 1, 1), 2), dtype=torch.float64, device=dev)
+                self.lib.qsp_seq_prepare(_p(target[b0:b1]), _p(bonds[b0:b1]), n, L, D, layers, max_bond, cutoff,
+                                         overlaps_gap, flags, _p(c_ov), _p(c_dis), _p(c_G), _p(c_kind), _p(c_sv),
+                                         _p(fin[b0:b1]) if want_final else None,
+                                         _p(finb[b0:b1]) if want_final else None, _p(status[b0:b1]), _p(work), nb, stream)
+                if not whole:
+                    ov[:, b0:b1] = c_ov
+                    dis[:, b0:b1] = c_dis
+                    G[:, b0:b1] = c_G
+                    kind[:, b0:b1] = c_kind
+                    sv[:, b0:b1] = c_sv
+                    for t in (c_ov, c_dis, c_G, c_kind, c_sv):
+                        t.record_stream(torch.cuda.current_stream(dev))
+        if two:
+            for s_ in self._side:
+                e = torch.cuda.Event()
+                e.record(s_)
+                cur.wait_event(e)
         return SeqResult(overlaps=ov, dis_overlaps=dis, G=G, kind=kind, d2_svals=sv, status=status, final_mps=fin,
                          final_bonds=finb, layers=layers, overlaps_gap=overlaps_gap)
 

@@ -190,7 +190,10 @@ class HostBatchPipeline:
     def __init__(self, L, D, num_seq_layers, max_bond_dim, chunk, device="cuda:0", overlaps_gap=4):
         self.dev = torch.device(device)
         self.L, self.D, self.layers, self.mb, self.chunk, self.gap = L, D, num_seq_layers, int(max_bond_dim), chunk, overlaps_gap
-        self.eng = Engine(device)       # layer loop (main stream)
+        # layer loops of consecutive chunks alternate between two compute streams (own workspaces): the tail of one
+        # chunk's persistent sweep kernels is filled by the next chunk's
+        self.eng = [Engine(device), Engine(device)]
+        self.s_c = [torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)]
         self.eng_in = Engine(device)    # input pipeline (its own workspace: runs concurrently on the side stream)
         self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
         self.buf = [(torch.empty((chunk, L, D, 2, D), dtype=torch.complex128, device=self.dev),
@@ -229,7 +232,6 @@ class HostBatchPipeline:
                             "kind": torch.empty((layers, n, L), dtype=torch.int32, **pin),
                             "status": torch.empty((n,), dtype=torch.int32, **pin)})
         self.h2d_bytes = self.d2h_bytes = 0
-        main = torch.cuda.current_stream(self.dev)
         free = [None, None]
         ready = self._stage_in(*host_chunks[0], 0, None)
         for k, (hm, _) in enumerate(host_chunks):
@@ -237,13 +239,15 @@ class HostBatchPipeline:
             nxt = None
             if k + 1 < len(host_chunks):  # next chunk's copy + preparation go under this chunk's layer loop
                 nxt = self._stage_in(*host_chunks[k + 1], 1 - slot, free[1 - slot])
-            main.wait_event(ready)
+            cs = self.s_c[slot]
             m, b, st = self.buf[slot]
             n = hm.shape[0]
-            res = self.eng.seq_prepare(m[:n], b[:n], layers, max_bond=self.mb, overlaps_gap=self.gap, chunk=n)
-            res.status |= st[:n]
-            done = torch.cuda.Event()
-            done.record(main)
+            with torch.cuda.stream(cs):
+                cs.wait_event(ready)
+                res = self.eng[slot].seq_prepare(m[:n], b[:n], layers, max_bond=self.mb, overlaps_gap=self.gap, chunk=n)
+                res.status |= st[:n]
+                done = torch.cuda.Event()
+                done.record(cs)
             free[slot] = done
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(done)
@@ -254,7 +258,8 @@ class HostBatchPipeline:
                     self.d2h_bytes += src.numel() * src.element_size()
             ready = nxt
         self.s_out.synchronize()
-        main.synchronize()
+        for cs in self.s_c:
+            cs.synchronize()
         return out
 
     @staticmethod
