@@ -139,6 +139,17 @@ int qsp_encoded_overlap(const qsp_c128* G, const int32_t* kind, int n, const qsp
                         const int32_t* target_bonds, int B, int L, int D, double cutoff, qsp_c128* result,
                         int32_t* status, void* work, size_t work_bytes, void* stream);
 
+/* Statevector of the emitted circuit on the device -- the cross-check the reference runs on qiskit-aer for small
+ * registers (qsp/q_circs/qiskit_circuit.py:52-67), batched.  state[B][2^L] complex128, axis i of the (2,)*L tensor =
+ * qubit i.  qsp_circuit_statevector: |psi_b> = U_0 .. U_{n-1} |0..0> from the layer-major outputs of qsp_seq_prepare
+ * (layers in reverse order, sites ascending, a two-qubit gate of site it on the qiskit qubit list [it+1, it], a
+ * one-qubit gate on [it]: qiskit_circuit.py:38-48).  qsp_statevector_apply: one gate on qubits [q_lo, q_hi] (matrix
+ * index 2*bit(q_hi) + bit(q_lo); q_lo = -1: one-qubit gate on q_hi, top-left 2x2 block) on every instance; gates is one
+ * shared 4x4 (per_instance = 0) or [B][4][4]; kind (optional, [B]): 0 skip / 1 one-qubit on q_hi / 2 two-qubit. */
+int qsp_statevector_apply(qsp_c128* state, int B, int L, const qsp_c128* gates, int per_instance, const int32_t* kind, int q_hi,
+                          int q_lo, void* stream);
+int qsp_circuit_statevector(const qsp_c128* G, const int32_t* kind, int n, int B, int L, qsp_c128* state, void* stream);
+
 /* The whole layer loop of sequential_unitary_circuit (sequential.py:42-85) for a batch.
  *   target / target_bonds : right-canonical normalised MPS (qsp_prepare_target output), D-padded;
  *                           every bond must stay <= D at every layer start (with

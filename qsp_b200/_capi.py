@@ -39,6 +39,8 @@ _SIGNATURES = {
     "qsp_prepare_target": (_i, [_p, _p, _i, _i, _i, _d, _p, _p, _sz, _p]),
     "qsp_encoded_overlap_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "qsp_encoded_overlap": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _d, _p, _p, _p, _sz, _p]),
+    "qsp_statevector_apply": (_i, [_p, _i, _i, _p, _i, _p, _i, _i, _p]),
+    "qsp_circuit_statevector": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "qsp_seq_prepare_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "qsp_set_profile_buffer": (None, [_p]),
     "qsp_seq_prepare": (_i, [_p, _p, _i, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -9,7 +9,21 @@
 
 #include "qsp_sweeps.cuh"
 #include "qsp_big_sweeps.cuh"
+
+// NVTX ranges per layer / sweep of the layer loop (header-only NVTX 3: a no-op unless a profiler is attached)
+#ifndef QSP_EMU
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#else
+struct NvtxRange {
+  explicit NvtxRange(const char*) {}
+};
+#endif
 #include "qsp_unitaries.cuh"
+#include "qsp_circuit.cuh"
 
 #ifdef QSP_EMU
 thread_local emu::Block* emu::g_blk = nullptr;
@@ -626,6 +640,44 @@ extern "C" int qsp_overlap(const qsp_c128* a, const int32_t* bonds_a, int D_a, c
 }
 
 // ------------------------------------------------------------------------------------
+// statevector of the emitted circuit (qiskit_circuit.py:34-70)
+// ------------------------------------------------------------------------------------
+extern "C" int qsp_statevector_apply(qsp_c128* state, int B, int L, const qsp_c128* gates, int per_instance, const int32_t* kind,
+                                     int q_hi, int q_lo, void* stream) {
+  if (!state || !gates || B <= 0 || L <= 0 || L > 30 || q_hi < 0 || q_hi >= L || q_lo >= L || q_lo == q_hi) return QSP_ERR_ARG;
+  if (q_lo < 0 && kind) return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  const long tot = (long)B << (L >= 2 ? L - 2 : 0);
+  const int grid = (int)imax(1, (int)((tot + 255) / 256 < (long)d.sms * 16 ? (tot + 255) / 256 : (long)d.sms * 16));
+  QSP_LAUNCH(k_sv_gate, grid, 256, 0, (qsp_stream_t)stream, (cplx*)state, B, L, (const cplx*)gates, per_instance ? 16L : 0L, kind, 1L,
+             q_hi, q_lo);
+  ++g_launches;
+  return check_launch();
+}
+// |psi_b> = U_0 ... U_{n-1} |0..0> for the gate layers G[n][B][L][4][4], kind[n][B][L] of a batch: layers in reverse
+// order, sites ascending, a two-qubit gate of site `it` on [it+1, it], a one-qubit gate on [it] (qiskit_circuit.py:38-48)
+extern "C" int qsp_circuit_statevector(const qsp_c128* G, const int32_t* kind, int n, int B, int L, qsp_c128* state, void* stream) {
+  if (!G || !kind || !state || n <= 0 || B <= 0 || L <= 0 || L > 30) return QSP_ERR_ARG;
+  DevInfo d = dev_info();
+  const long tot = (long)B << L;
+  QSP_LAUNCH(k_sv_init, (int)imin((int)((tot + 255) / 256 < 65535 ? (tot + 255) / 256 : 65535), d.sms * 16), 256, 0, (qsp_stream_t)stream,
+             (cplx*)state, B, L);
+  ++g_launches;
+  // one launch per (layer, site): instance b applies G[layer][b][site] with its own kind (segments differ per instance)
+  for (int it_layer = n - 1; it_layer >= 0; --it_layer)
+    for (int it = 0; it < L; ++it) {
+      const qsp_c128* g = G + ((size_t)it_layer * B * L + it) * 16;
+      const int32_t* kd = kind + (size_t)it_layer * B * L + it;
+      const long tg = (long)B << (L >= 2 ? L - 2 : 0);
+      const int grid = (int)imax(1, (int)((tg + 255) / 256 < (long)d.sms * 16 ? (tg + 255) / 256 : (long)d.sms * 16));
+      QSP_LAUNCH(k_sv_gate, grid, 256, 0, (qsp_stream_t)stream, (cplx*)state, B, L, (const cplx*)g, (long)L * 16, kd, (long)L, it,
+                 it + 1 < L ? it + 1 : -1);
+      ++g_launches;
+    }
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------
 // input pipeline: MPSPreparation.__init__ + sequential.py:38-40
 // ------------------------------------------------------------------------------------
 static size_t mps_bytes(int B, int L, int D) { return align_up((size_t)B * L * D * 2 * D * sizeof(cplx)); }
@@ -673,12 +725,12 @@ extern "C" int qsp_prepare_target(qsp_c128* mps, int32_t* bonds, int B, int L, i
 // Encoded state U_0..U_k|0..0> (core.py:217-221).  Every forward layer doubles the bonds exactly
 // (k_expand_forward) and keeps the state right canonical and normalised, so the reference's
 // compress('right') after each layer (core.py:140, cutoff only) changes nothing but the bond
-// sizes.  Mode A (2^layers <= QSP_ENC_CAP): buffers of 2^layers, no compression at all.  Mode B (more
-// layers, any chain): like the reference the state is compressed (cutoff only) whenever the next
-// doubling would not fit the De-padded buffers; the compressed bonds must fit De / 2 (QSP_ST_BOND_OVERFLOW
-// otherwise).  The exact rank of an L-site state is at most 2^(L/2), so short chains get by with
+// sizes.  Mode A (2^layers <= QSP_ENC_CAP, i.e. up to 11 layers): buffers of 2^layers, no compression at
+// all.  Mode B (more layers, any chain): like the reference the state is compressed (cutoff only) whenever
+// the next doubling would not fit the De-padded buffers; the compressed bonds must fit De / 2 = 1024
+// (QSP_ST_BOND_OVERFLOW otherwise; the reference's Heisenberg L=32 benchmark reaches 517 at 12 layers).  The exact rank of an L-site state is at most 2^(L/2), so short chains get by with
 // De = 2^(L/2+1).
-#define QSP_ENC_CAP 256
+#define QSP_ENC_CAP 2048  // (134 MB per site and instance at this padding: large batches are chunked by the caller)
 struct EncPlan {
   int De;        // padded bond of both encoded-state buffers
   int rank_cap;  // bound on the bonds after a compression
@@ -858,15 +910,25 @@ extern "C" int qsp_seq_prepare(const qsp_c128* target, const int32_t* target_bon
   if (overlaps) dev_fill_nan(overlaps, (long)layers * B, st);
 
   for (int it = 0; it < layers; ++it) {
+    char nm[48];
+    snprintf(nm, sizeof(nm), "qsp layer %d", it);
+    NvtxRange layer_range(nm);
     qsp_c128* Git = G + (size_t)it * B * L * 16;
     int32_t* kit = kind + (size_t)it * B * L;
     double* sv = d2_svals ? d2_svals + (size_t)it * B * (L - 1) * 2 : nullptr;
     // generate_bond_d_unitary (core.py:12-22): compress('right', max_bond=2) = left sweep + truncating right sweep
-    if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, scratch, sb, stream))) return rc;
-    if ((rc = qsp_right_compress(psi, psib, D, d2, d2b, 2, B, L, 2, cutoff, 1, sv, 2, nullptr, status, scratch, sb,
-                                 stream)))
-      return rc;
-    if ((rc = qsp_generate_unitaries(d2, d2b, B, L, Git, kit, status, stream))) return rc;
+    {
+      NvtxRange r("left_canonize");
+      if ((rc = qsp_left_canonize(psi, psib, B, L, D, status, scratch, sb, stream))) return rc;
+    }
+    {
+      NvtxRange r("d2_truncation + unitaries");
+      if ((rc = qsp_right_compress(psi, psib, D, d2, d2b, 2, B, L, 2, cutoff, 1, sv, 2, nullptr, status, scratch, sb,
+                                   stream)))
+        return rc;
+      if ((rc = qsp_generate_unitaries(d2, d2b, B, L, Git, kit, status, stream))) return rc;
+    }
+    NvtxRange fused_range("inverse layer + re-truncation sweep");
     // sequential.py:51-57 in ONE sweep: apply_inverse_unitary_layer_on_wfn on the left-canonical psi (exact,
     // left canonical, never materialised) fused with [right_canonize; compress('right', max_bond)];
     // right_canonize(normalize); compress()  -- the fused gate-apply-and-split kernel

@@ -183,6 +183,33 @@ class Engine:
     def mps_scale(self, x, bx, alpha):
         self.lib.qsp_mps_scale(_p(x), _p(bx), x.shape[2], _p(alpha), x.shape[0], x.shape[1], _runtime.current_stream_ptr())
 
+    # ---- statevector of the emitted circuits (qiskit_circuit.py:52-67), batched -------------------
+    def circuit_statevector(self, G, kind):
+        """|psi_b> = U_0 .. U_{n-1} |0..0> for G[n, B, L, 4, 4], kind[n, B, L] -> state[B, 2^L] (axis i of the (2,)*L view
+        = qubit i).  16 bytes * 2^L per instance: the caller chunks the batch."""
+        n, B, L = G.shape[0], G.shape[1], G.shape[2]
+        state = self.empty_c(B, 1 << L)
+        self.lib.qsp_circuit_statevector(_p(G.contiguous()), _p(kind.contiguous()), n, B, L, _p(state), _runtime.current_stream_ptr())
+        return state
+
+    def statevector_apply(self, state, gate, q_hi, q_lo=-1):
+        """one gate (4x4 tensor, a one-qubit gate in its top-left 2x2 block) on qubits [q_lo, q_hi] of state[B, 2^L]"""
+        B, L = state.shape[0], int(state.shape[1]).bit_length() - 1
+        self.lib.qsp_statevector_apply(_p(state), B, L, _p(gate), 0, None, q_hi, q_lo, _runtime.current_stream_ptr())
+
+    @staticmethod
+    def dense_from_packed(mps, bonds):
+        """dense amplitudes [B, 2^L] of packed MPS (plumbing for the circuit cross-check only; L <= ~24)"""
+        B, L, D = mps.shape[0], mps.shape[1], mps.shape[2]
+        ar = torch.arange(D, device=mps.device)
+        t = None
+        for i in range(L):
+            ml = (ar[None, :] < bonds[:, i, None]).to(mps.dtype)        # [B, D] live left extent
+            mr = (ar[None, :] < bonds[:, i + 1, None]).to(mps.dtype)
+            a = torch.nan_to_num(mps[:, i]) * ml[:, :, None, None] * mr[:, None, None, :]
+            t = a[:, 0] if t is None else torch.einsum("bxl,blpr->bxpr", t, a).reshape(B, -1, D)
+        return t[:, :, 0]
+
     # ---- the layer loop ---------------------------------------------------------------------
     def seq_prepare(self, target, bonds, layers, max_bond=0, cutoff=CUTOFF, overlaps_gap=4, second_pass=False,
                     encoded=True, want_final=False, chunk=None, overlap_chunks=True):

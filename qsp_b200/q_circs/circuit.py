@@ -51,21 +51,35 @@ class GateListCircuit:
         return {"size": 11 * n2 + n1, "num_nonlocal_gates": 3 * n2}
 
     def statevector(self, device="cuda:0"):
-        """|psi> = circuit |0..0>, returned with axis i = qubit i (torch tensor on `device`)."""
+        """|psi> = circuit |0..0> on the device (k_sv_gate, one launch per gate), returned as a (2,)*L torch tensor with
+        axis i = qubit i -- the cross-check the reference runs on qiskit-aer (qiskit_circuit.py:57-61)."""
         import torch
 
         L = self.num_qubits
-        psi = torch.zeros((2,) * L, dtype=torch.complex128, device=device)
-        psi[(0,) * L] = 1.0
-        for u, q in self.gates:
-            g = torch.from_numpy(u).to(device)
-            if len(q) == 1:
-                psi = torch.movedim(torch.tensordot(g, psi, dims=([1], [q[0]])), 0, q[0])
-            else:
-                hi, lo = q[1], q[0]  # matrix index = 2*bit(q[1]) + bit(q[0])
-                g4 = g.reshape(2, 2, 2, 2)
-                psi = torch.movedim(torch.tensordot(g4, psi, dims=([2, 3], [hi, lo])), (0, 1), (hi, lo))
-        return psi
+        if str(device) == "cpu":  # explicit host request (tiny registers in the CPU test-suite): plain tensordot
+            psi = torch.zeros((2,) * L, dtype=torch.complex128)
+            psi[(0,) * L] = 1.0
+            for u, q in self.gates:
+                g = torch.from_numpy(u)
+                if len(q) == 1:
+                    psi = torch.movedim(torch.tensordot(g, psi, dims=([1], [q[0]])), 0, q[0])
+                else:
+                    hi, lo = q[1], q[0]
+                    psi = torch.movedim(torch.tensordot(g.reshape(2, 2, 2, 2), psi, dims=([2, 3], [hi, lo])), (0, 1), (hi, lo))
+            return psi
+        from ..engine import Engine
+
+        eng = Engine(device)
+        psi = torch.zeros((1, 1 << L), dtype=torch.complex128, device=eng.device)
+        psi[0, 0] = 1.0
+        if self.gates:
+            g4 = np.zeros((len(self.gates), 4, 4), np.complex128)
+            for k, (u, q) in enumerate(self.gates):
+                g4[k, : u.shape[0], : u.shape[1]] = u
+            gd = torch.from_numpy(g4).to(eng.device)
+            for k, (_, q) in enumerate(self.gates):  # matrix index = 2*bit(q[1]) + bit(q[0])
+                eng.statevector_apply(psi, gd[k], q[-1], q[0] if len(q) == 2 else -1)
+        return psi.reshape((2,) * L)
 
 
 class CxU3Circuit:
@@ -171,6 +185,9 @@ class CxU3Circuit:
         return "\n".join(out) + "\n"
 
 
+SIM_MAX_QUBITS = 20  # the reference simulates up to 16 qubits on qiskit-aer (qiskit_circuit.py:53)
+
+
 def _dense_from_mps(arrays, device):
     import torch
 
@@ -201,12 +218,10 @@ def circuit_from_unitary_layers(unitary_layers, L, target_mps=None, device="cuda
         circ = shadow = CxU3Circuit.from_gate_list(circ)
     overlap_from_seq_circ = None
     arrays = getattr(target_mps, "arrays", None)
-    if L <= 16 and arrays is not None:
+    if L <= SIM_MAX_QUBITS and arrays is not None:
         import torch
 
-        # 2^L amplitudes: below ~4k the simulation is launch-bound on a GPU, so tiny registers run on the host
-        sim_dev = "cpu" if L <= 12 else device
-        vec = shadow.statevector(sim_dev)
-        orig = _dense_from_mps(arrays, sim_dev)
+        vec = shadow.statevector(device)  # hand-written statevector kernel (csrc/qsp_circuit.cuh), 16 MB at L = 20
+        orig = _dense_from_mps(arrays, device)
         overlap_from_seq_circ = float(torch.abs(torch.sum(torch.conj(orig) * vec)).item())
     return circ, overlap_from_seq_circ

@@ -126,6 +126,7 @@ class BatchedMPSPreparation:
         if not prepared:
             self.status = self.engine.prepare_target(self.mps, self.bonds)
         self.seq_data = None
+        self._circs = {}
 
     def sequential_unitary_circuit(self, num_seq_layers, do_compression=False, max_bond_dim=None, overlaps_gap=4,
                                    second_pass=False, chunk=None, check=False):
@@ -145,6 +146,7 @@ class BatchedMPSPreparation:
                                       second_pass=second_pass, chunk=chunk)
         res.status |= self.status  # a target flagged during preparation stays flagged
         self.seq_data = res
+        self._circs = {}
         if check:
             bad = torch.nonzero(res.status & ST_FATAL).flatten()
             if bad.numel():
@@ -166,6 +168,33 @@ class BatchedMPSPreparation:
             raise RuntimeError(f"{bad.size} of {self.B} instances failed, first: instance {int(bad[0])} "
                                f"status {int(r['status'][bad[0]]):#x} (QSP_ST_* in include/qsp_b200.h)")
         return r["overlaps"][-1], r
+
+    def circuit(self, b):
+        """The {cx, u3} circuit of instance b (qsp/q_circs/qiskit_circuit.py:34-50), materialised on demand from the
+        device-resident gates (the path returns `(overlap, circ)`; a batch keeps its circuits lazy)."""
+        from .q_circs import circuit_from_unitary_layers
+
+        if b not in self._circs:
+            self._circs[b] = circuit_from_unitary_layers(self.unitaries(b), self.L, None)[0]
+        return self._circs[b]
+
+    def circuit_overlaps(self, chunk=None):
+        """|<target_b| circuit_b |0..0>| for every instance (the reference's Aer cross-check, qiskit_circuit.py:52-67, on
+        the device and for registers up to 20 qubits): statevectors from the gate layers (k_sv_gate), dense targets from
+        the prepared MPS.  Returns a float64 tensor [B]."""
+        from .q_circs.circuit import SIM_MAX_QUBITS
+
+        if self.L > SIM_MAX_QUBITS:
+            raise ValueError(f"statevector cross-check is limited to {SIM_MAX_QUBITS} qubits (L = {self.L})")
+        res = self.seq_data
+        chunk = chunk or max(1, (1 << 28) >> self.L)
+        out = torch.empty(self.B, dtype=torch.float64, device=self.engine.device)
+        for b0 in range(0, self.B, chunk):
+            b1 = min(self.B, b0 + chunk)
+            sv = self.engine.circuit_statevector(res.G[:, b0:b1], res.kind[:, b0:b1])
+            tg = self.engine.dense_from_packed(self.mps[b0:b1], self.bonds[b0:b1])
+            out[b0:b1] = (tg.conj() * sv).sum(dim=1).abs()
+        return out
 
     def unitaries(self, b):
         """Reference-style list of Gs_lst layers for instance b."""

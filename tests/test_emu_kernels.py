@@ -292,8 +292,10 @@ def test_status_bits_and_error_codes(drv):
     a, b = pack_batch(tg, 4)
     r = drv.seq_prepare(a, b, 2, max_bond=0)  # no compression: bonds want to double beyond D=4
     assert r["status"][0] & 2
-    # unsupported size is reported before anything is launched
-    assert drv.lib.qsp_seq_prepare_workspace_bytes(1, 10, 512, 2, 512, 0) == 0
+    # no bond is too large any more (the batched large-bond path takes over beyond one SM); a bad shape is refused
+    # before anything is launched
+    assert drv.lib.qsp_seq_prepare_workspace_bytes(1, 10, 512, 2, 512, 0) > 0
+    assert drv.lib.qsp_seq_prepare_workspace_bytes(0, 10, 8, 2, 8, 0) == 0
     assert drv.lib._qsp_left_canonize(None, None, 1, 4, 4, None, None, 0, None) == 1
 
 
@@ -450,3 +452,29 @@ def test_big_left_canonize_multipanel(big_path):
             assert np.abs(q.conj().T @ q - np.eye(q.shape[1])).max() < 1e-12
         if m is not wide:  # (with dependent columns the QR is not unique)
             assert max(np.abs(x - y).max() for x, y in zip(ref, g)) < 1e-12
+
+
+def test_circuit_statevector_kernel(drv):
+    """k_sv_gate: the batched statevector of the gate layers equals the oracle's dense simulation (qiskit ordering:
+    layers reversed, sites ascending, a 4x4 on [it+1, it], qiskit_circuit.py:38-48), including segmented layers with
+    one-qubit gates in the middle of the chain; a shared explicit gate list (qsp_statevector_apply) agrees too."""
+    L = 7
+    tgs = [_prepared(O.random_mps(L, 4, 41)), _prepared(edge_cases()["product_state"][0] + edge_cases()["product_state"][0][:2])]
+    a, b = pack_batch(tgs, 4)
+    r = drv.seq_prepare(a, b, 3, max_bond=4)
+    state = np.full((2, 1 << L), np.nan + 0j)
+    drv.lib.qsp_circuit_statevector(drv.p(r["G"]), drv.p(r["kind"]), 3, 2, L, drv.p(state), None)
+    for k in range(2):
+        layers = [gates_to_layers(r["G"][j, k], r["kind"][j, k]) for j in range(3)]
+        ref = O.circuit_statevector(layers, L).reshape(-1)
+        assert np.abs(state[k] - ref).max() < 1e-13
+        assert abs(abs(np.vdot(O.mps_to_dense(tgs[k]).reshape(-1), state[k])) - abs(r["overlaps"][2, k])) < 1e-12
+    # explicit gates, shared by the batch: instance 0's circuit applied to |0..0> on both rows
+    st2 = np.zeros((2, 1 << L), np.complex128)
+    st2[:, 0] = 1.0
+    for j in reversed(range(3)):
+        for it in range(L):
+            g = np.ascontiguousarray(r["G"][j, 0, it])
+            assert r["kind"][j, 0, it] in (1, 2)
+            drv.lib.qsp_statevector_apply(drv.p(st2), 2, L, drv.p(g), 0, None, it, it + 1 if r["kind"][j, 0, it] == 2 else -1, None)
+    assert np.abs(st2[0] - state[0]).max() < 1e-13 and np.abs(st2[1] - state[0]).max() < 1e-13

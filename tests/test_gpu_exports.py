@@ -302,3 +302,51 @@ def test_overlapped_chunks_match_single_call(drv):
     assert pipe.h2d_bytes == B * (L * chi * 2 * chi * 16 + (L + 1) * 4)
     assert torch.equal(out["G"], one.G.cpu()) and torch.equal(out["kind"], one.kind.cpu()) and torch.equal(out["status"], one.status.cpu())
     assert torch.equal(torch.view_as_real(out["dis_overlaps"]), torch.view_as_real(one.dis_overlaps.cpu()))
+
+
+def test_batched_circuits_and_statevector_check(drv):
+    """(overlap, circ) for a batch: circuits are materialised on demand from the device-resident gates, and the
+    reference's statevector cross-check (qiskit_circuit.py:52-67) runs on the device for all instances at 18 qubits
+    (the reference stops at 16)."""
+    import torch
+
+    from qsp_b200.tsp import BatchedMPSPreparation
+
+    L, chi, layers, B = 18, 8, 3, 5
+    raws = [O.random_mps(L, chi, 400 + s) for s in range(B)]
+    prep = BatchedMPSPreparation(raws, shape="lpr")
+    ov, res = prep.sequential_unitary_circuit(layers, do_compression=True, max_bond_dim=chi, check=True)
+    co = prep.circuit_overlaps(chunk=2)
+    torch.cuda.synchronize()
+    assert float((co - ov.abs()).abs().max()) < 1e-11
+    circ = prep.circuit(3)
+    assert prep.circuit(3) is circ and set(circ.count_ops()) == {"u3", "cx"}
+    assert circ.source.size() == layers * L and circ.source.num_nonlocal_gates() == layers * (L - 1)
+    sv = circ.statevector().reshape(-1)  # the synthesised {cx, u3} circuit on the device kernel
+    tgt = prep.engine.dense_from_packed(prep.mps[3:4], prep.bonds[3:4])[0]
+    assert abs(abs(complex((tgt.conj() * sv).sum())) - abs(complex(ov[3]))) < 1e-10
+
+
+def test_heisenberg_twelve_layers_reference_benchmark(drv):
+    """the reference's own benchmark (examples/benchmarks.py:57-60): Heisenberg L=32 ground state, max_bond_dim=256,
+    12 layers -- working bond 256 (large-bond kernels), encoded state of rank 517 beyond the doubling buffers.  Golden
+    values: the oracle with the same completion convention (tests/golden/make_heisenberg_canonical.py, four CPU minutes)."""
+    import json
+    import os
+
+    from qsp_b200.mps import MPSState
+    from qsp_b200.tsp import MPSPreparation
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ref = json.load(open(os.path.join(gold, "heisenberg_canonical_12layers.json")))
+    z = np.load(os.path.join(gold, "heisenberg_L32.npz"))
+    b, m = z["bonds"], z["mps"]
+    raw = [m[i, : b[i], :, : b[i + 1]].astype(np.complex128) for i in range(len(b) - 1)]
+    prep = MPSPreparation(MPSState(raw), shape="lpr")
+    ov, circ = prep.sequential_unitary_circuit(12, do_compression=True, max_bond_dim=256)
+    d = prep.seq_data
+    assert d["it_Ds"] == ref["it_Ds"]
+    assert np.abs(np.abs(d["overlaps"]) - np.array(ref["abs_overlaps"])).max() < 1e-7
+    assert np.abs(np.abs(d["disentangled_mps_overlaps"]) - np.array(ref["abs_disentangled_overlaps"])).max() < 1e-7
+    assert abs(abs(ov) - ref["abs_overlaps"][-1]) < 1e-7 and 0.70 < abs(ov) < 0.80  # pickle (LAPACK convention): 0.748
+    assert circ.source.size() == 12 * 32

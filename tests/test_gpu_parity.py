@@ -305,6 +305,14 @@ def test_pipeline_ten_layers_on_14_sites(drv):
     _check_pipeline(drv, tg, 10, 8, 8, check_svals=False)
 
 
+def test_pipeline_twelve_layers_on_18_sites(drv):
+    """more layers than the 2048-padded encoded-state buffers can double through (2^12 > 2048) on a chain whose exact
+    rank (2^9) does not fit the small kernels: the encoded state is compressed between layers like the reference does
+    (core.py:139-141), through the large-bond left-canonise / block-Jacobi kernels at bonds up to 512."""
+    tg = [_prepared(O.random_mps(18, 8, 99))]
+    _check_pipeline(drv, tg, 12, 8, 8, check_svals=False, same_convention=False)
+
+
 @pytest.mark.parametrize("name", list(edge_cases()))
 def test_pipeline_edge_cases(drv, name):
     """product states, rank-deficient padding, degenerate Schmidt values, L = 1, 2, 3, real input."""
