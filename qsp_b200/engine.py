@@ -158,8 +158,8 @@ class Engine:
         B, L, Din = mps.shape[0], mps.shape[1], mps.shape[2]
         out, bo, status = self.empty_c(B, L, Dout, 2, Dout), self.zeros_i(B, L + 1), self.zeros_i(B)
         fn = self.lib.qsp_apply_inverse_layer if inverse else self.lib.qsp_apply_forward_layer
-        fn(_p(mps), _p(bonds), Din, _p(G.contiguous()), _p(kind.contiguous()), _p(out), _p(bo), Dout, B, L, _p(status),
-           _runtime.current_stream_ptr())
+        G, kind = G.contiguous(), kind.contiguous()  # (held: a temporary freed before the launch could be re-used)
+        fn(_p(mps), _p(bonds), Din, _p(G), _p(kind), _p(out), _p(bo), Dout, B, L, _p(status), _runtime.current_stream_ptr())
         return out, bo, status
 
     def overlap(self, a, ba, b, bb):
@@ -189,7 +189,8 @@ class Engine:
         = qubit i).  16 bytes * 2^L per instance: the caller chunks the batch."""
         n, B, L = G.shape[0], G.shape[1], G.shape[2]
         state = self.empty_c(B, 1 << L)
-        self.lib.qsp_circuit_statevector(_p(G.contiguous()), _p(kind.contiguous()), n, B, L, _p(state), _runtime.current_stream_ptr())
+        G, kind = G.contiguous(), kind.contiguous()  # (held until the launches are enqueued)
+        self.lib.qsp_circuit_statevector(_p(G), _p(kind), n, B, L, _p(state), _runtime.current_stream_ptr())
         return state
 
     def statevector_apply(self, state, gate, q_hi, q_lo=-1):

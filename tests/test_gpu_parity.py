@@ -273,7 +273,9 @@ def test_full_size_batch_properties(drv):
     assert int(res.status.max()) == 0
     for k in (77, 149):
         assert torch.equal(res.G[:, k], res.G[:, 0]) and torch.equal(res.dis_overlaps[:, k], res.dis_overlaps[:, 0])
-        assert torch.equal(res.overlaps[:, k], res.overlaps[:, 0]) and torch.equal(res.final_mps[k], res.final_mps[0])
+        assert torch.equal(res.overlaps[:, k], res.overlaps[:, 0]) and torch.equal(res.final_bonds[k], res.final_bonds[0])
+        fk, f0 = unpack_batch(res.final_mps[[k, 0]].cpu().numpy(), res.final_bonds[[k, 0]].cpu().numpy())  # (live extents only:
+        assert all(np.array_equal(x, y) for x, y in zip(fk, f0))                                         # padding is never written)
     G = res.G.reshape(-1, 4, 4)
     kind = res.kind.reshape(-1)
     eye = torch.eye(4, dtype=G.dtype, device=G.device)
@@ -283,7 +285,8 @@ def test_full_size_batch_properties(drv):
     assert float((g1 @ g1.conj().transpose(1, 2) - eye[:2, :2]).abs().max()) < 1e-12
     assert int((kind == 2).sum()) == layers * B * (L - 1) and int((kind == 1).sum()) == layers * B
     # site 0 is the orthogonality centre of the right-canonical result: its norm is the norm of the state
-    nrm = res.final_mps[:, 0].abs().pow(2).sum(dim=(1, 2, 3))
+    live = torch.arange(chi, device=res.final_mps.device)[None, :] < res.final_bonds[:, 1, None]  # (padding is never written)
+    nrm = (res.final_mps[:, 0, 0].abs().pow(2) * live[:, None, :]).nan_to_num().sum(dim=(1, 2))
     assert float((nrm - 1.0).abs().max()) < 1e-12
     assert float(res.dis_overlaps[1].abs().mean()) > float(res.dis_overlaps[0].abs().mean())
 
@@ -297,6 +300,14 @@ def test_pipeline_large_bonds(drv, L, chi, layers, no_comp):
         _check_pipeline(drv, tg, layers, 0, min(chi * 2 ** layers, 2 ** (L // 2)))
     else:
         _check_pipeline(drv, tg, layers, chi, chi)
+
+
+def test_pipeline_chi256_L40_two_layers(drv):
+    """BASELINE configs[4] bond dimension on a 40-site chain, two layers (teacher-forced: the device's unitaries through
+    the oracle's literal steps; about three CPU minutes): left canonisation by blocked Householder QR, D=2 truncation and
+    the fused 2 chi -> chi sweep by the block Jacobi SVD on the FP64 tensor cores, 512 x 512 matrices in the bulk."""
+    tg = [_prepared(O.random_mps(40, 256, 98))]
+    _check_pipeline(drv, tg, 2, 256, 256, same_convention=False)
 
 
 def test_pipeline_ten_layers_on_14_sites(drv):
