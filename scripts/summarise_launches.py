@@ -42,8 +42,8 @@ order = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
 
 out = [f"# ncu launch list, {tag} (own kernels only)", "",
        "command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-       f"-k regex:^k_ -c 400 --csv python bench.py --batch {batch} --steps 1 --warmup 1 --no-cpu-baseline --no-e2e`",
-       f"(after the same command exited 0 without ncu; B200, L=100 chi=64 4 layers, {batch} instances per step; "
+       f"-k regex:^k_ -c 400 --csv python bench.py --batch-total {2 * batch} --steps 1 --warmup 1 --no-cpu-baseline --no-e2e`",
+       f"(after the same command exited 0 without ncu; B200, L=100 chi=64 4 layers, two chunks of {batch} instances per step; "
        "per-launch times are cold-cache and serialised - compare SHARES, not absolutes)", "",
        f"{len(launches)} launches captured (warm-up step + timed step + the kernel-roofline replay of one layer), "
        f"total {total:.1f} ms", "",
@@ -68,9 +68,9 @@ for k, e in list(launches.items())[:30]:
     out.append(f"| {k} | {e['name']} | {e['grid']} | {e['block']} | {e['ms']:.3f} | {(e['rd'] + e['wr']) / 1e6:.1f} |")
 open(os.path.join(root, "profiles", f"{tag}_launches.md"), "w").write("\n".join(out) + "\n")
 
-tj = os.path.join(root, "profiles", f"{tag}_traffic.json")
+tj = os.path.join(root, "profiles", "traffic.json")  # read by bench.py (roofline.traffic)
 old = json.load(open(tj)) if os.path.exists(tj) else {}
-old.update({"kernel": "k_right_compress(fused inverse layer + 2chi->chi)", "config": "L100 chi64 layers4", "batch": batch,
+old.update({"kernel": "k_right_compress(fused inverse layer + 2chi->chi)", "config": "L100 chi64", "batch": batch,
             "dram_bytes_per_launch": mean_b, "dram_bytes_per_instance": mean_b / batch,
             "source": f"profiles/{tag}_launches.csv", "share_of_own_kernel_time_ncu": share})
 json.dump(old, open(tj, "w"), indent=1)
