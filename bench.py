@@ -335,7 +335,7 @@ def main():
     per_inst = L * chi * chi * 32
     # instances per qsp_seq_prepare call: bounded so that two pipeline slots + a workspace fit beside the targets
     a.chunk_eff = a.chunk if a.chunk > 0 else int(max(1, min(n_local, 592 if chi >= 64 else 2048, max(32, (12 << 30) // per_inst))))
-    if a.chunk <= 0 and a.chunk_eff >= n_local and n_local >= 64:
+    if a.chunk <= 0 and a.chunk_eff >= n_local and n_local >= (8 if chi > 64 else 64):
         a.chunk_eff = (n_local + 1) // 2  # at least two chunks: their sweep kernels overlap on two streams (Engine.seq_prepare)
 
     tgt, tb, host = local_inputs(torch, a, dev, b0, b1, want_host=not a.no_e2e)

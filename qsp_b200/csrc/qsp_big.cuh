@@ -55,7 +55,7 @@ __host__ __device__ inline size_t big_gemm_smem_bytes() {
 }
 
 // grid.x = ndesc * tiles_m * tiles_n (tile index fastest); CTAs whose tile lies outside the live extent exit
-__global__ void __launch_bounds__(QSP_BIG_NT) k_big_gemm(const BigGemm* __restrict__ gd, int tiles_m, int tiles_n) {
+__global__ void __launch_bounds__(QSP_BIG_NT, 2) k_big_gemm(const BigGemm* __restrict__ gd, int tiles_m, int tiles_n) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int per = tiles_m * tiles_n;
   const int di = blockIdx.x / per, t = blockIdx.x - di * per;
@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_gemm(const BigGemm* __restri
   if (g.m <= 0 || g.n <= 0 || i0 >= g.m || j0 >= g.n) return;
   cplx* sm = (cplx*)QSP_SMEM_BASE();
   // two buffers of As[64][LD] (element (row, k)) and Bs[64][LD] (element (col, k))
-  cplx* As[2] = {sm, sm + (QSP_GB_TM + QSP_GB_TN) * QSP_GB_LD};
-  cplx* Bs[2] = {As[0] + QSP_GB_TM * QSP_GB_LD, As[1] + QSP_GB_TM * QSP_GB_LD};
+  constexpr int kBuf = (QSP_GB_TM + QSP_GB_TN) * QSP_GB_LD;
+  cplx* const As0 = sm;
+  cplx* const Bs0 = sm + QSP_GB_TM * QSP_GB_LD;
   // loader mapping: 512 elements of A and of B per k-chunk, two of each per thread
   const bool kfastA = (g.sAk == 1), kfastB = (g.sBk == 1);
   int ar[2], ak[2], bc[2], bk[2];
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_gemm(const BigGemm* __restri
   auto sstore = [&](int buf) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      As[buf][ar[u] * QSP_GB_LD + ak[u]] = ra[u];
-      Bs[buf][bc[u] * QSP_GB_LD + bk[u]] = rb[u];
+      As0[buf * kBuf + ar[u] * QSP_GB_LD + ak[u]] = ra[u];
+      Bs0[buf * kBuf + bc[u] * QSP_GB_LD + bk[u]] = rb[u];
     }
   };
   // warp tile: 16 rows x 32 columns = 2 x 4 complex 8x8 tiles; warps 4 (m) x 2 (n)
@@ -120,9 +121,9 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_gemm(const BigGemm* __restri
     for (int ks = 0; ks < QSP_GB_TK; ks += 4) {
       cplx af[2], bf[4];
 #pragma unroll
-      for (int a = 0; a < 2; ++a) af[a] = As[buf][(wm + a * 8 + fr) * QSP_GB_LD + ks + fk];
+      for (int a = 0; a < 2; ++a) af[a] = As0[buf * kBuf + (wm + a * 8 + fr) * QSP_GB_LD + ks + fk];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bf[b] = Bs[buf][(wn + b * 8 + fr) * QSP_GB_LD + ks + fk];
+      for (int b = 0; b < 4; ++b) bf[b] = Bs0[buf * kBuf + (wn + b * 8 + fr) * QSP_GB_LD + ks + fk];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll

@@ -717,3 +717,63 @@ __global__ void k_big_lc_qdesc(BigLCArgs P, const BigLCState* __restrict__ S, in
   gW[inst] = g;
   gC[inst] = h;
 }
+
+// ----------------------------------------------------------------------------------
+// transfer-matrix overlap sum_x a(x) conj(b(x)) for large bonds (norm_mps_ovrlap, helper_routines.py:65-73): the two
+// environment updates of a site as batched tensor-core GEMMs,
+//   T[x,(p,y')] = sum_y E[x,y] conj(B[y,p,y']),     E'[x',y'] = sum_(x,p) A[x,p,x'] T[(x,p),y']
+// ----------------------------------------------------------------------------------
+struct BigOvArgs {
+  const cplx* a;
+  const int32_t* bonds_a;
+  int Da;
+  const cplx* b;
+  const int32_t* bonds_b;
+  int Db, B, L;
+  cplx* result;
+  cplx* work;  // per instance: E0, E1 (Da x Db), T (Da x 2 Db)
+  long work_stride;
+};
+__host__ __device__ inline long big_ov_work_elems(int Da, int Db) { return 4L * Da * Db + 64; }
+
+// gT[2 * inst + p], gE[inst]: operands of site i (ping-pong environments: E_i lives in slot i & 1)
+__global__ void k_big_ov_site(BigOvArgs P, int i, BigGemm* __restrict__ gT, BigGemm* __restrict__ gE) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= P.B) return;
+  const int32_t* ba = P.bonds_a + (long)inst * (P.L + 1);
+  const int32_t* bb = P.bonds_b + (long)inst * (P.L + 1);
+  cplx* E0 = P.work + (long)inst * P.work_stride;
+  cplx* E1 = E0 + (long)P.Da * P.Db;
+  cplx* T = E1 + (long)P.Da * P.Db;
+  cplx* E = (i & 1) ? E1 : E0;
+  cplx* En = (i & 1) ? E0 : E1;
+  if (i == 0) E[0] = cmake(1.0, 0.0);  // bonds[0] == 1 on both sides
+  const int xa = ba[i], xb = bb[i], ya = ba[i + 1], yb = bb[i + 1];
+  const cplx* Ai = P.a + ((long)inst * P.L + i) * ((long)P.Da * 2 * P.Da);
+  const cplx* Bi = P.b + ((long)inst * P.L + i) * ((long)P.Db * 2 * P.Db);
+  BigGemm g;
+  for (int p = 0; p < 2; ++p) {
+    memset(&g, 0, sizeof(g));
+    g.A = E, g.sAr = xb, g.sAk = 1;
+    g.B = Bi + (long)p * P.Db, g.sBk = 2L * P.Db, g.sBc = 1, g.conjB = 1;
+    g.C = T + (long)p * yb, g.sCr = 2L * yb, g.sCc = 1;
+    g.m = xa, g.n = yb, g.k = xb;
+    gT[2 * inst + p] = g;
+  }
+  memset(&g, 0, sizeof(g));
+  g.A = Ai, g.sAr = 1, g.sAk = P.Da;
+  g.B = T, g.sBk = yb, g.sBc = 1;
+  g.C = En, g.sCr = yb, g.sCc = 1;
+  g.m = ya, g.n = yb, g.k = 2 * xa;
+  gE[inst] = g;
+  if (i == P.L - 1) {
+    // nothing: the result is read by k_big_ov_done after the last GEMM
+  }
+}
+__global__ void k_big_ov_done(BigOvArgs P) {
+  const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= P.B) return;
+  const cplx* E0 = P.work + (long)inst * P.work_stride;
+  const cplx* E1 = E0 + (long)P.Da * P.Db;
+  P.result[inst] = (P.L & 1) ? E1[0] : E0[0];  // E_L lives in slot L & 1
+}

@@ -618,8 +618,13 @@ extern "C" int qsp_apply_forward_layer(const qsp_c128* in, const int32_t* bonds_
 }
 
 static const int kOverlapNT = 256;
+static bool overlap_is_big(int D_a, int D_b) { return g_force_big || imax(D_a, D_b) > 64; }
+static size_t big_overlap_bytes(int B, int D_a, int D_b) {
+  return align_up((size_t)3 * B * sizeof(BigGemm)) + align_up((size_t)B * big_ov_work_elems(D_a, D_b) * sizeof(cplx));
+}
 extern "C" size_t qsp_overlap_workspace_bytes(int B, int L, int D_a, int D_b) {
   (void)L;
+  if (B > 0 && overlap_is_big(D_a, D_b)) return big_overlap_bytes(B, D_a, D_b);
   DevInfo d = dev_info();
   int grid = grid_for(B, 2, d);
   return align_up((size_t)grid * overlap_work_elems(D_a, D_b) * sizeof(cplx));
@@ -628,6 +633,28 @@ extern "C" int qsp_overlap(const qsp_c128* a, const int32_t* bonds_a, int D_a, c
                            const int32_t* bonds_b, int D_b, int B, int L, qsp_c128* result, void* work,
                            size_t work_bytes, void* stream) {
   if (!a || !bonds_a || !b || !bonds_b || !result || !work || B <= 0 || L <= 0) return QSP_ERR_ARG;
+  if (overlap_is_big(D_a, D_b)) {  // environments as batched tensor-core GEMMs (qsp_big_sweeps.cuh)
+    if (work_bytes < big_overlap_bytes(B, D_a, D_b)) return QSP_ERR_WORKSPACE;
+    BigGemm* gT = (BigGemm*)work;
+    BigGemm* gE = gT + 2 * (size_t)B;
+    BigOvArgs P;
+    P.a = (const cplx*)a, P.bonds_a = bonds_a, P.Da = D_a, P.b = (const cplx*)b, P.bonds_b = bonds_b, P.Db = D_b;
+    P.B = B, P.L = L, P.result = (cplx*)result;
+    P.work = (cplx*)((char*)work + align_up((size_t)3 * B * sizeof(BigGemm)));
+    P.work_stride = big_ov_work_elems(D_a, D_b);
+    qsp_stream_t st = (qsp_stream_t)stream;
+    int rc;
+    for (int i = 0; i < L; ++i) {
+      // upper bounds of the extents: bond j <= min(D, 2^j, 2^(L-j)) cannot be assumed for an arbitrary input: use D
+      QSP_LAUNCH(k_big_ov_site, (B + 127) / 128, 128, 0, st, P, i, gT, gE);
+      ++g_launches;
+      if ((rc = launch_big_gemm(gT, 2 * B, D_a, D_b, st))) return rc;
+      if ((rc = launch_big_gemm(gE, B, D_a, D_b, st))) return rc;
+    }
+    QSP_LAUNCH(k_big_ov_done, (B + 127) / 128, 128, 0, st, P);
+    ++g_launches;
+    return check_launch();
+  }
   DevInfo d = dev_info();
   int grid = grid_for(B, 2, d);
   long stride = overlap_work_elems(D_a, D_b);

@@ -4,6 +4,7 @@ is a call into libqsp_b200.so (include/qsp_b200.h).
 Layout: a batch of B MPS of L sites is `mps[B, L, D, 2, D]` complex128 with the
 live bond extents in `bonds[B, L+1]` int32; element (l, p, r) of a site is mps[b, i, l, p, r].
 """
+import concurrent.futures
 import contextlib
 import ctypes
 
@@ -246,7 +247,7 @@ class Engine:
             ev0.record(cur)
             for s_ in self._side:
                 s_.wait_event(ev0)
-        for ci, b0 in enumerate(starts):
+        def run_chunk(ci, b0):
             b1 = min(B, b0 + chunk)
             n = b1 - b0
             nb = self.seq_workspace_bytes(n, L, D, layers, max_bond, flags)
@@ -278,6 +279,22 @@ class Engine:
                     sv[:, b0:b1] = c_sv
                     for t in (c_ov, c_dis, c_G, c_kind, c_sv):
                         t.record_stream(torch.cuda.current_stream(dev))
+
+        if two and D > 64:
+            # the large-bond sweeps read a convergence flag per Jacobi sweep on the host: one host thread per stream keeps
+            # both streams fed (the library's state is per thread; ctypes releases the GIL during the call)
+            def worker(k):
+                torch.cuda.set_device(dev)
+                for ci, b0 in enumerate(starts):
+                    if ci % 2 == k:
+                        run_chunk(ci, b0)
+
+            with concurrent.futures.ThreadPoolExecutor(2) as ex:
+                for f in [ex.submit(worker, 0), ex.submit(worker, 1)]:
+                    f.result()
+        else:
+            for ci, b0 in enumerate(starts):
+                run_chunk(ci, b0)
         if two:
             for s_ in self._side:
                 e = torch.cuda.Event()

@@ -108,6 +108,14 @@ class MPSPreparation:
         return complex(res[0].item())
 
 
+def _synthesise_circuit(job):
+    """worker of BatchedMPSPreparation.circuits: gate layers of one instance -> CxU3Circuit (host-side, no CUDA)"""
+    from .q_circs import circuit_from_unitary_layers
+
+    G, kind, L = job
+    return circuit_from_unitary_layers([gates_to_gs_lst(G[k], kind[k]) for k in range(G.shape[0])], L, None)[0]
+
+
 class BatchedMPSPreparation:
     """Many independent targets of equal length, resident on one GPU (SURVEY.md section 8e:
     instances are the only parallel axis of this path)."""
@@ -177,6 +185,27 @@ class BatchedMPSPreparation:
         if b not in self._circs:
             self._circs[b] = circuit_from_unitary_layers(self.unitaries(b), self.L, None)[0]
         return self._circs[b]
+
+    def circuits(self, indices=None, workers=None):
+        """{cx, u3} circuits of many instances at once: the gates are fetched from the device in one copy and the host-side
+        synthesis (q_circs.kak, ~45 us per gate) is spread over `workers` processes (default: the host cores)."""
+        import multiprocessing as mp
+        import os
+
+        idx = list(range(self.B)) if indices is None else [int(i) for i in indices]
+        todo = [b for b in idx if b not in self._circs]
+        if todo:
+            G = self.seq_data.G[:, todo].cpu().numpy()
+            kind = self.seq_data.kind[:, todo].cpu().numpy()
+            jobs = [(G[:, j], kind[:, j], self.L) for j in range(len(todo))]
+            workers = workers or min(len(todo), len(os.sched_getaffinity(0)))
+            if workers > 1:
+                with mp.get_context("fork").Pool(workers) as pool:
+                    out = pool.map(_synthesise_circuit, jobs, chunksize=max(1, len(jobs) // (4 * workers)))
+            else:
+                out = [_synthesise_circuit(j) for j in jobs]
+            self._circs.update(zip(todo, out))
+        return [self._circs[b] for b in idx]
 
     def circuit_overlaps(self, chunk=None):
         """|<target_b| circuit_b |0..0>| for every instance (the reference's Aer cross-check, qiskit_circuit.py:52-67, on

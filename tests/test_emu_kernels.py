@@ -49,6 +49,7 @@ def test_large_bond_left_canonize_path(big_path):
     assert drv.lib.qsp_left_canonize_workspace_bytes(2, 7, 6) > 0
     test_left_canonize(drv)
     test_prepare_target(drv)
+    test_overlap(drv)  # environments as batched tensor-core GEMMs
     test_layer_loop(drv, "compressed")
     assert drv.lib._qsp_left_canonize(drv.p(np.zeros(4 * 2 * 4 * 4, np.complex128)), drv.p(np.ones(5, np.int32)), 1, 4, 4,
                                       None, None, 0, None) == 3  # QSP_ERR_WORKSPACE

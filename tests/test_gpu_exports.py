@@ -322,6 +322,9 @@ def test_batched_circuits_and_statevector_check(drv):
     circ = prep.circuit(3)
     assert prep.circuit(3) is circ and set(circ.count_ops()) == {"u3", "cx"}
     assert circ.source.size() == layers * L and circ.source.num_nonlocal_gates() == layers * (L - 1)
+    many = prep.circuits(workers=2)  # bulk synthesis over host processes
+    assert len(many) == B and many[3] is circ and all(c.source.size() == layers * L for c in many)
+    assert many[1].count_ops() == prep.circuit(1).count_ops()
     sv = circ.statevector().reshape(-1)  # the synthesised {cx, u3} circuit on the device kernel
     tgt = prep.engine.dense_from_packed(prep.mps[3:4], prep.bonds[3:4])[0]
     assert abs(abs(complex((tgt.conj() * sv).sum())) - abs(complex(ov[3]))) < 1e-10
