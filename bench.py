@@ -295,7 +295,10 @@ def local_inputs(torch, a, dev, b0, b1, want_host):
     for c0 in range(0, n, ck):
         c1 = min(n, c0 + ck)
         if want_host:
-            hm = torch.empty(raw[c0:c1].shape, dtype=raw.dtype, pin_memory=True)
+            try:
+                hm = torch.empty(raw[c0:c1].shape, dtype=raw.dtype, pin_memory=True)
+            except RuntimeError:  # host cannot pin that much: pageable memory still gives an (slower) end-to-end number
+                hm = torch.empty(raw[c0:c1].shape, dtype=raw.dtype)
             hb = torch.empty(bonds[c0:c1].shape, dtype=bonds.dtype, pin_memory=True)
             hm.copy_(raw[c0:c1])
             hb.copy_(bonds[c0:c1])
