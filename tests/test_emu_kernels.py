@@ -479,3 +479,10 @@ def test_circuit_statevector_kernel(drv):
             assert r["kind"][j, 0, it] in (1, 2)
             drv.lib.qsp_statevector_apply(drv.p(st2), 2, L, drv.p(g), 0, None, it, it + 1 if r["kind"][j, 0, it] == 2 else -1, None)
     assert np.abs(st2[0] - state[0]).max() < 1e-13 and np.abs(st2[1] - state[0]).max() < 1e-13
+
+
+@pytest.mark.parametrize("name", ["product_state", "ghz_degenerate_schmidt", "two_sites"])
+def test_edge_cases_through_large_bond_kernels(big_path, name):
+    """segment boundaries (one-qubit gates inside the chain), collapsed bonds, degenerate Schmidt pairs and the shortest
+    chains through the batched large-bond sweeps (their per-site branches differ from the one-CTA kernels)"""
+    test_edge_cases(big_path, name)
