@@ -18,8 +18,6 @@ Site order is recovered from the physical index name 'k{i}' (tids are NOT in sit
 order in the P4 file).
 """
 import os
-import pickle
-import re
 import sys
 
 import numpy as np
@@ -27,69 +25,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-class _Stub:
-    def __init__(self, *a, **k):
-        self._args, self._kw = a, k
-
-    def __setstate__(self, st):
-        self._state = st
-
-
-_cache = {}
-
-
-class _Unpickler(pickle.Unpickler):
-    def find_class(self, module, name):
-        if module.startswith("numpy") or module in ("builtins", "collections", "copyreg", "_codecs"):
-            return super().find_class(module, name)
-        key = (module, name)
-        if key not in _cache:
-            _cache[key] = type(name, (_Stub,), {"_mod": module})
-        return _cache[key]
-
-
-def _load(path):
-    with open(path, "rb") as f:
-        return _Unpickler(f).load()
-
-
-def _tensor_state(t):
-    st = t._state
-    if isinstance(st, dict):
-        return st["_data"] if "_data" in st else st["data"], st.get("_inds", st.get("inds"))
-    return st[0], st[1]
-
-
-def mps_arrays_lpr(mps_stub):
-    """-> list of L arrays shaped (l, 2, r), l=1 at site 0 and r=1 at site L-1."""
-    st = mps_stub._state
-    tmap = st["tensor_map"]
-    sites = {}
-    for _, t in tmap.items():
-        data, inds = _tensor_state(t)
-        ks = [ix for ix in inds if re.fullmatch(r"k\d+", ix)]
-        assert len(ks) == 1, inds
-        sites[int(ks[0][1:])] = (np.asarray(data), tuple(inds))
-    L = len(sites)
-    out = []
-    # bond between i and i+1 is the index shared by the two tensors
-    for i in range(L):
-        data, inds = sites[i]
-        k = f"k{i}"
-        left = right = None
-        if i > 0:
-            left = (set(inds) & set(sites[i - 1][1])).pop()
-        if i < L - 1:
-            right = (set(inds) & set(sites[i + 1][1])).pop()
-        order = [ix for ix in (left, k, right) if ix is not None]
-        a = np.transpose(data, [inds.index(ix) for ix in order])
-        if left is None:
-            a = a[None, ...]
-        if right is None:
-            a = a[..., None]
-        assert a.ndim == 3 and a.shape[1] == 2, a.shape
-        out.append(np.ascontiguousarray(a))
-    return out
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from qsp_b200.io import load_pickle_without_quimb as _load  # noqa: E402  (the product's quimb-free pickle loader)
+from qsp_b200.io import mps_arrays_lpr, tensor_state as _tensor_state  # noqa: E402
 
 
 def unitaries_to_arrays(layers):

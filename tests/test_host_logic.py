@@ -90,3 +90,64 @@ def test_flop_model_reproduces_survey_numbers():
     assert abs(flop_model.bytes_per_mps(100, 64, 4) / 1.71e9 - 1) < 0.01
     assert abs(flop_model.flops_per_mps(50, 16, 4)["total"] / 2.33e9 - 1) < 0.01
     assert abs(flop_model.flops_per_mps(200, 256, 8)["total"] / 8.40e13 - 1) < 0.01
+
+
+def test_load_qsp_pickle_without_quimb(tmp_path):
+    """qsp_b200.io: the reference's example pickles hold quimb objects; the loader stubs every foreign class and rebuilds
+    the site tensors from the index names (tensor ids deliberately shuffled, end tensors 2-D as quimb stores them)."""
+    import pickle
+    import sys
+    import types
+
+    import numpy as np
+
+    from qsp_b200.io import load_qsp_pickle
+
+    mod = types.ModuleType("quimb.tensor.tensor_core")
+    mod1d = types.ModuleType("quimb.tensor.tensor_1d")
+
+    class Tensor:
+        def __init__(self, data, inds):
+            self.st = (data, inds, ("I0",), None)
+
+        def __getstate__(self):
+            return self.st
+
+        def __setstate__(self, st):
+            self.st = st
+
+    class MatrixProductState:
+        def __init__(self, tmap):
+            self.__dict__["d"] = {"tensor_map": tmap, "_L": len(tmap), "_site_ind_id": "k{}"}
+
+        def __getstate__(self):
+            return self.d
+
+        def __setstate__(self, st):
+            self.__dict__["d"] = st
+
+    Tensor.__module__, Tensor.__qualname__ = "quimb.tensor.tensor_core", "Tensor"
+    MatrixProductState.__module__, MatrixProductState.__qualname__ = "quimb.tensor.tensor_1d", "MatrixProductState"
+    mod.Tensor, mod1d.MatrixProductState = Tensor, MatrixProductState
+    names = {"quimb": types.ModuleType("quimb"), "quimb.tensor": types.ModuleType("quimb.tensor"),
+             "quimb.tensor.tensor_core": mod, "quimb.tensor.tensor_1d": mod1d}
+    rng = np.random.default_rng(0)
+    arrs = [rng.standard_normal((1 if i == 0 else 3, 2, 1 if i == 3 else 3)) for i in range(4)]
+    tens = {}
+    for i, a in enumerate(arrs):
+        inds = ([f"b{i-1}"] if i > 0 else []) + [f"k{i}"] + ([f"b{i}"] if i < 3 else [])
+        data = a.reshape([s for s, keep in zip(a.shape, (i > 0, True, i < 3)) if keep])
+        perm = list(range(data.ndim))[::-1]  # stored in a different index order than (l, p, r)
+        tens[97 - 13 * i] = Tensor(np.transpose(data, perm), tuple(inds[j] for j in perm))
+    sys.modules.update(names)
+    try:
+        path = tmp_path / "state.pkl"
+        with open(path, "wb") as f:
+            pickle.dump({"quimb_mps": MatrixProductState(tens), "SeqU_data": {"overlaps": [0.5]}}, f)
+    finally:
+        for k in names:
+            sys.modules.pop(k, None)
+    mps, raw = load_qsp_pickle(str(path))
+    assert mps.L == 4 and raw["SeqU_data"]["overlaps"] == [0.5]
+    for a, b in zip(mps.arrays, arrs):
+        assert a.shape == b.shape and np.array_equal(a, b)
