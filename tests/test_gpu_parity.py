@@ -302,6 +302,18 @@ def test_pipeline_large_bonds(drv, L, chi, layers, no_comp):
         _check_pipeline(drv, tg, layers, chi, chi)
 
 
+@pytest.mark.parametrize("L,chi,layers,mb", [(14, 70, 2, 70), (16, 97, 2, 97), (13, 33, 2, 0), (15, 65, 2, 40)])
+def test_pipeline_large_bonds_unaligned(drv, L, chi, layers, mb):
+    """bonds that are no multiple of the 16-row Jacobi blocks, the 32-column TMA chunks or the 64-wide GEMM tiles (ragged
+    tails everywhere in the large-bond kernels); mb = 0: no compression, the working bond doubles past 64 (33 -> 128);
+    mb < chi: truncating re-compression"""
+    tg = [_prepared(O.random_mps(L, chi, 120 + s)) for s in range(2)]
+    if mb == 0:
+        _check_pipeline(drv, tg, layers, 0, min(chi * 2 ** layers, 2 ** (L // 2)))
+    else:
+        _check_pipeline(drv, tg, layers, mb, chi)
+
+
 def test_pipeline_chi256_L40_two_layers(drv):
     """BASELINE configs[4] bond dimension on a 40-site chain, two layers (teacher-forced: the device's unitaries through
     the oracle's literal steps; about three CPU minutes): left canonisation by blocked Householder QR, D=2 truncation and
