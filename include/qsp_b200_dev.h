@@ -33,6 +33,7 @@ int qsp_dmma_probe(double* out, int blocks, int threads, int iters, void* stream
  * qsp_big_jacobi: block one-sided Jacobi SVD on the FP64 tensor cores; the rows of W[B][nrows][ldw] are orthogonalised
  * in place (ldw and ndotp multiples of 32, zero padded); sweeps[B], ok[B] (device); work: qsp_big_jacobi_work_bytes().
  * qsp_big_gemm: batched DMMA GEMM C[b] = op(A[b]) op(B[b]) (row-major, trans / conj flags); work: batch * 128 bytes. */
+void qsp_big_tuning(int update_splits, int gram_splits); /* tuning hook: column splits of the block-Jacobi launches (0 = automatic) */
 size_t qsp_big_jacobi_work_bytes(int nrows, int ldw, int B);
 int qsp_big_jacobi(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int* sweeps, int* ok, void* work, void* stream);
 int qsp_big_gemm(const qsp_c128* A, int transA, int conjA, const qsp_c128* Bm, int transB, int conjB, qsp_c128* C, int m, int n,

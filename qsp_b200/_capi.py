@@ -55,6 +55,7 @@ _DEV_SIGNATURES = {
     "qsp_jacobi_bench": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "qsp_dfma_probe": (_i, [_p, _i, _i, _i, _p]),
     "qsp_dmma_probe": (_i, [_p, _i, _i, _i, _p]),
+    "qsp_big_tuning": (None, [_i, _i]),
     "qsp_big_jacobi_work_bytes": (_sz, [_i, _i, _i]),
     "qsp_big_jacobi": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "qsp_big_gemm": (_i, [_p, _i, _i, _p, _i, _i, _p, _i, _i, _i, _i, _p, _p]),

@@ -217,23 +217,25 @@ __device__ __forceinline__ void big_split_range(int nch, int sp, int splits, int
 }
 
 __host__ __device__ inline size_t big_ring_bytes() { return (size_t)QSP_BIG_NS * QSP_BIG_PR * QSP_BIG_LDS * sizeof(cplx); }
-__host__ __device__ inline size_t big_gram_smem_bytes() { return big_ring_bytes() + QSP_BIG_NS * 16 + 64; }
+__host__ __device__ inline size_t big_gram_smem_bytes() { return big_ring_bytes() + 2 * QSP_BIG_NS * 32 + 64; }
 __host__ __device__ inline size_t big_solve_smem_bytes() { return (size_t)QSP_BIG_PR * QSP_BIG_LDY * sizeof(cplx) + 64 * sizeof(double) + 64; }
 __host__ __device__ inline size_t big_update_smem_bytes() {
-  return big_ring_bytes() + (size_t)QSP_BIG_PR * QSP_BIG_LDJ * sizeof(cplx) + QSP_BIG_NS * 16 + 64;
+  return big_ring_bytes() + (size_t)QSP_BIG_PR * QSP_BIG_LDJ * sizeof(cplx) + 2 * QSP_BIG_NS * 32 + 64;
 }
 
 // TMA ring of 32-row x 32-column chunks of one panel: warp 0 issues one bulk copy per live row, chunks are consumed in
 // issue order (stage = n % NS, parity = (n / NS) & 1)
 struct BigRing {
   cplx* ring;
-  qsp_mbar* bars;
+  qsp_mbar* full;   // [NS] bytes landed
+  qsp_mbar* empty;  // [NS] all warps have finished reading the stage
   const cplx* W;
   long ldw;
   int myrow, nlive, issued, consumed;
   __device__ __forceinline__ void init(char* smem_ring, qsp_mbar* b, const BigJac& J, const BigTask& t) {
     ring = (cplx*)smem_ring;
-    bars = b;
+    full = b;
+    empty = b + QSP_BIG_NS;
     W = J.W;
     ldw = J.ldw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -248,27 +250,38 @@ struct BigRing {
       }
     fence_proxy_async();
     if (tid == 0) {
-      for (int s = 0; s < QSP_BIG_NS; ++s) mbar_init(&bars[s]);
+      for (int s = 0; s < QSP_BIG_NS; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], (int)(blockDim.x >> 5));
+      }
       fence_mbar_init();
     }
     __syncthreads();
   }
+  // warp 0 (all lanes call): waits until every warp has released the stage's previous chunk, then refills it
   __device__ __forceinline__ void issue(int chunk) {
-    const int stage = issued++ % QSP_BIG_NS;
+    const int n = issued++, stage = n % QSP_BIG_NS;
     if ((threadIdx.x >> 5) == 0) {
       const int lane = threadIdx.x & 31;
-      if (lane == 0) mbar_expect_tx(&bars[stage], (unsigned)(nlive * QSP_BIG_CK * sizeof(cplx)));
+      if (n >= QSP_BIG_NS) mbar_wait(&empty[stage], ((n / QSP_BIG_NS) - 1) & 1);
+      if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)(nlive * QSP_BIG_CK * sizeof(cplx)));
       __syncwarp();
       if (myrow >= 0)
         tma_load_1d(ring + ((long)stage * QSP_BIG_PR + lane) * QSP_BIG_LDS, W + (long)myrow * ldw + (long)chunk * QSP_BIG_CK,
-                    (unsigned)(QSP_BIG_CK * sizeof(cplx)), &bars[stage]);
+                    (unsigned)(QSP_BIG_CK * sizeof(cplx)), &full[stage]);
     }
   }
   __device__ __forceinline__ const cplx* wait_next() {
     const int stage = consumed % QSP_BIG_NS;
-    mbar_wait(&bars[stage], (consumed / QSP_BIG_NS) & 1);
-    ++consumed;
+    mbar_wait(&full[stage], (consumed / QSP_BIG_NS) & 1);
     return ring + (long)stage * QSP_BIG_PR * QSP_BIG_LDS;
+  }
+  // the calling warp has finished reading the chunk returned by the last wait_next()
+  __device__ __forceinline__ void release() {
+    const int stage = consumed % QSP_BIG_NS;
+    ++consumed;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stage]);
   }
 };
 
@@ -321,9 +334,10 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_jac_gram(const BigJac* __res
       for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
         for (int tj = ti; tj < 4; ++tj, ++q) dmma_8x8x4(acc[q].i0, acc[q].i1, -f[ti].x, f[tj].y);
+      R.release();  // (the fragments are in registers: the stage may be refilled)
     }
-    __syncthreads();
   }
+  __syncthreads();
   // ---- reduce the eight partial Gram matrices (deterministic tree through the idle ring) ---
   double* part = (double*)R.ring;  // [warp][tile][4][32 lanes]
   for (int half = 4; half >= 1; half >>= 1) {
@@ -603,6 +617,7 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_jac_update(const BigJac* __r
         dmma_8x8x4(o[0].i0, o[0].i1, ji[0][ks], bq.x);
         dmma_8x8x4(o[1].i0, o[1].i1, ji[1][ks], bq.x);
       }
+      R.release();  // (all fragments of the chunk are loaded: the stage may be refilled)
 #pragma unroll
       for (int u2 = 0; u2 < 2; ++u2)
         if (orow[u2] >= 0) {
@@ -611,7 +626,6 @@ __global__ void __launch_bounds__(QSP_BIG_NT) k_big_jac_update(const BigJac* __r
           dst[1] = cmake(o[u2].r1, o[u2].i1);
         }
     }
-    __syncthreads();
   }
 }
 

@@ -360,20 +360,36 @@ static int launch_big_gemm(const BigGemm* gd, int ndesc, int m_max, int n_max, q
 }
 // block Jacobi SVD of the B matrices described by jd (device); nrows_max / len_max bound every instance's extents.
 // jw: scratch of big_jacobi_scratch_bytes(B, nrows_max, len_max) (partial Gram matrices, pair unitaries, skip flags)
-static int big_jacobi_splits(int len_max) { return imax(1, imin(4, len_max / (4 * QSP_BIG_CK))); }
+#ifdef QSP_DEV_BUILD
+static int g_big_splits = 0, g_big_gsplits = 0;  // tuning hooks (qsp_big_tuning)
+#else
+static const int g_big_splits = 0, g_big_gsplits = 0;
+#endif
+// Column splits of the tensor-core launches of a round: enough CTAs to keep 148 SMs two deep (about 1024 update CTAs, 512
+// Gram CTAs -- the Gram launch pays a cross-warp reduction per CTA), at least two chunks per CTA.  Measured at 32 x (512 x 512):
+// (update, gram) = (2, 1) 82.9 ms, (4, 2) 85.8 ms, (1, 1) 87.8 ms, (8, 2) 93.4 ms.
+static void big_jacobi_splits(int B, int nrows_max, int len_max, int* usplits, int* gsplits) {
+  const int nblk = ((nrows_max + QSP_BIG_RB - 1) / QSP_BIG_RB + 1) & ~1;
+  const long tasks = (long)B * (nblk / 2);
+  const int cap = imax(1, len_max / (2 * QSP_BIG_CK));
+  *usplits = g_big_splits ? g_big_splits : imax(1, imin(imin(8, cap), (int)((1024 + tasks - 1) / tasks)));
+  *gsplits = g_big_gsplits ? g_big_gsplits : imax(1, imin(imin(4, cap), (int)((512 + tasks - 1) / tasks)));
+}
 static size_t big_jacobi_scratch_bytes(int B, int nrows_max, int len_max) {
   const int nblk = ((nrows_max + QSP_BIG_RB - 1) / QSP_BIG_RB + 1) & ~1;
   const size_t tasks = (size_t)B * (nblk / 2), tile = (size_t)QSP_BIG_PR * QSP_BIG_PR * sizeof(cplx);
-  return align_up(tasks * big_jacobi_splits(len_max) * tile) + align_up(tasks * tile) + align_up(tasks * sizeof(int));
+  return align_up(tasks * 4 * tile) + align_up(tasks * tile) + align_up(tasks * sizeof(int));  // (up to four Gram partials)
 }
 static int big_jacobi_run(BigJac* jd, int B, int nrows_max, int len_max, int* flags, int* any, int* sweeps, void* jw, qsp_stream_t st) {
   if (nrows_max < 2) return QSP_OK;
   const int nblk = ((nrows_max + QSP_BIG_RB - 1) / QSP_BIG_RB + 1) & ~1;
-  const int pairs = nblk / 2, rounds = nblk - 1, splits = big_jacobi_splits(len_max);
-  const int gsplits = imax(1, splits / 2);  // the Gram launch pays a cross-warp reduction per CTA: split it less
+  const int pairs = nblk / 2, rounds = nblk - 1;
+  int splits, gsplits;
+  big_jacobi_splits(B, nrows_max, len_max, &splits, &gsplits);
+  gsplits = imin(gsplits, 4);
   const size_t tasks = (size_t)B * pairs, tile = (size_t)QSP_BIG_PR * QSP_BIG_PR * sizeof(cplx);
   cplx* Gp = (cplx*)jw;
-  cplx* Jg = (cplx*)((char*)jw + align_up(tasks * splits * tile));
+  cplx* Jg = (cplx*)((char*)jw + align_up(tasks * 4 * tile));
   int* skip = (int*)((char*)Jg + align_up(tasks * tile));
   QSP_PREP_KERNEL(k_big_jac_gram, big_gram_smem_bytes());
   QSP_PREP_KERNEL(k_big_jac_solve, big_solve_smem_bytes());

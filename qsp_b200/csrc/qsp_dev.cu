@@ -256,3 +256,9 @@ extern "C" int qsp_big_gemm(const qsp_c128* A, int transA, int conjA, const qsp_
   int rc = launch_big_gemm((const BigGemm*)work, batch, m, n, st);
   return rc ? rc : check_launch();
 }
+
+// tuning hook: column splits of the block-Jacobi update / Gram launches (0 = automatic)
+extern "C" void qsp_big_tuning(int update_splits, int gram_splits) {
+  g_big_splits = update_splits;
+  g_big_gsplits = gram_splits;
+}

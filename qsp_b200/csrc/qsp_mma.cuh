@@ -15,25 +15,35 @@
 #include <string.h>
 inline void dmma_8x8x4(double& c0, double& c1, double a, double b) { emu_dmma(c0, c1, a, b); }
 struct qsp_mbar {
-  long long pending;  // bytes still in flight (+ one "arrival" unit of 1 << 40 until expect_tx was called)
+  long long tx;    // bytes still expected in this phase (may go negative before expect_tx is seen)
+  int arrivals;    // arrivals still missing in this phase
+  int count;       // arrivals per phase
   int phase;
   int pad;
 };
-inline void mbar_init(qsp_mbar* m) {
-  m->pending = 1LL << 40;
-  m->phase = 0;
-}
-inline void mbar_complete(qsp_mbar* m, long long bytes) {
-  m->pending -= bytes;
-  if (m->pending == 0) {
+inline void mbar_check(qsp_mbar* m) {
+  if (m->arrivals == 0 && m->tx == 0) {
     m->phase ^= 1;
-    m->pending = 1LL << 40;
+    m->arrivals = m->count;
   }
 }
-inline void mbar_expect_tx(qsp_mbar* m, unsigned bytes) { mbar_complete(m, (1LL << 40) - (long long)bytes); }
+inline void mbar_init(qsp_mbar* m, int count = 1) {
+  m->tx = 0;
+  m->arrivals = m->count = count;
+  m->phase = 0;
+}
+inline void mbar_arrive(qsp_mbar* m) {
+  m->arrivals -= 1;
+  mbar_check(m);
+}
+inline void mbar_expect_tx(qsp_mbar* m, unsigned bytes) {
+  m->tx += bytes;
+  mbar_arrive(m);
+}
 inline void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, qsp_mbar* m) {
   memcpy(dst_smem, src_gmem, bytes);
-  mbar_complete(m, bytes);
+  m->tx -= bytes;
+  mbar_check(m);
 }
 inline void mbar_wait(qsp_mbar* m, int parity) {
   while (m->phase == parity) emu_spin_yield();
@@ -48,8 +58,12 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 }
 typedef unsigned long long qsp_mbar;  // 8-byte shared-memory mbarrier object
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(qsp_mbar* m) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(m)) : "memory");
+__device__ __forceinline__ void mbar_init(qsp_mbar* m, int count = 1) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(m)), "r"(count) : "memory");
+}
+// plain arrival (consumer side of a ring: "this warp has finished reading the stage")
+__device__ __forceinline__ void mbar_arrive(qsp_mbar* m) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(m)) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // orders this thread's generic-proxy shared-memory writes before later async-proxy (TMA) accesses to the same bytes

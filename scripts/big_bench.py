@@ -9,6 +9,8 @@ from qsp_b200 import _runtime
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 lib = _runtime.dev_lib()
+if len(sys.argv) > 4:
+    lib.qsp_big_tuning(int(sys.argv[3]), int(sys.argv[4]))  # column splits of the update / Gram launches
 dev = torch.device("cuda:0")
 p = lambda t: ctypes.c_void_p(t.data_ptr())
 s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
