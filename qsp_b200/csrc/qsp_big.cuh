@@ -26,7 +26,7 @@
 #define QSP_BIG_PR 32   // rows per block pair (panel)
 #define QSP_BIG_CK 32   // columns per streamed chunk (rows of W are zero-padded to a multiple of it)
 #define QSP_BIG_LDS 34  // shared row stride of a chunk (complex): 4 k-rows x 32 B hit distinct bank groups
-#define QSP_BIG_LDY 68  // shared row stride of Y = [L | J]
+#define QSP_BIG_LDY 69  // shared row stride of Y = [G or L | J] in the solve kernel (odd: rows and columns conflict free)
 #define QSP_BIG_LDJ 36  // shared row stride of J in the update kernel
 #define QSP_BIG_NS 4    // TMA ring stages (two chunks consumed between block barriers, two in flight)
 #define QSP_BIG_NT 256  // threads per CTA of the round and GEMM kernels
@@ -436,6 +436,89 @@ __global__ void __launch_bounds__(QSP_BIG_NT, 4) k_big_jac_solve(const BigJac* _
   if (tid == 0) {
     skip[task] = 0;
     if (maxratio > QSP_JAC_QUAD * QSP_JAC_QUAD) flags[inst] = 1;
+  }
+
+  // ---- well-scaled panel (row norms within 1e4 of each other): rotate G itself two-sidedly, G <- R G R^H.  g_pp, g_qq, g_pq
+  // ARE the Gram entries Hestenes' method reduces, so this is the same rotation sequence as the sweep on the rows of the
+  // Cholesky factor below, without the factorisation, the dot products and the shuffle reductions.  J is a product of exact
+  // plane rotations, so X <- J X stays an orthogonal transformation whatever rounding G accumulates, and convergence is
+  // always judged on a freshly computed Gram matrix; only the RELATIVE accuracy of entries far below the largest one is
+  // lost by updating G explicitly, which is why strongly graded (or rank deficient) panels take the Cholesky route. -------
+  if (warp == 0) {
+    double dmax = sd[lane], dmin = sd[lane] > 0.0 ? sd[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      dmax = fmax(dmax, shfl_xor_d(dmax, o));
+      dmin = fmin(dmin, shfl_xor_d(dmin, o));
+    }
+    if (lane == 0) sd[34] = (dmin >= 1e-8 * dmax) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (sd[34] != 0.0) {
+    for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT) {
+      const int i = idx / QSP_BIG_PR, k = idx - i * QSP_BIG_PR;
+      Y[i * QSP_BIG_LDY + QSP_BIG_PR + k] = cmake(i == k ? 1.0 : 0.0, 0.0);
+    }
+    const int team = tid >> 4, tl = tid & 15;  // 16 pairs x 16 lanes
+    volatile double* rotflag = sd + 33;
+    const bool bip = round > 0;
+    const int nr = bip ? QSP_BIG_RB : QSP_BIG_PR - 1;
+    for (int sw = 0; sw < J.inner; ++sw) {
+      if (tid == 0) *rotflag = 0.0;
+      __syncthreads();
+      for (int r = 0; r < nr; ++r) {
+        int a, b;
+        if (bip) {
+          a = team;
+          b = QSP_BIG_RB + ((team + r) & (QSP_BIG_RB - 1));
+        } else if (team == 0) {
+          a = QSP_BIG_PR - 1;
+          b = r;
+        } else {
+          a = (r + team) % (QSP_BIG_PR - 1);
+          b = (r + QSP_BIG_PR - 1 - team) % (QSP_BIG_PR - 1);
+        }
+        const int p = a < b ? a : b, q = a < b ? b : a;
+        const double al = Y[p * QSP_BIG_LDY + p].x, be = Y[q * QSP_BIG_LDY + q].x;
+        const cplx g = Y[p * QSP_BIG_LDY + q];
+        const double g2 = cabs2(g), ab = al * be;
+        const bool rot = ab > 1e-280 && g2 > J.tol2 * ab;
+        double cs = 1.0, sx = 0.0, sy = 0.0;
+        if (rot && tl == 0) jacobi_rotation(al, be, g.x, g.y, g2, cs, sx, sy);
+        cs = __shfl_sync(QSP_FULL_MASK, cs, 0, 16);
+        sx = __shfl_sync(QSP_FULL_MASK, sx, 0, 16);
+        sy = __shfl_sync(QSP_FULL_MASK, sy, 0, 16);
+        __syncthreads();  // every pair has read its three entries
+        if (rot) {        // rows p, q of [G | J]:  x' = cs x - se y,  y' = conj(se) x + cs y
+          cplx* xp = Y + p * QSP_BIG_LDY;
+          cplx* yq = Y + q * QSP_BIG_LDY;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const cplx x = xp[tl + 16 * u], y = yq[tl + 16 * u];
+            xp[tl + 16 * u] = cmake(cs * x.x - (sx * y.x - sy * y.y), cs * x.y - (sx * y.y + sy * y.x));
+            yq[tl + 16 * u] = cmake(cs * y.x + (sx * x.x + sy * x.y), cs * y.y + (sx * x.y - sy * x.x));
+          }
+          if (tl == 0) *rotflag = 1.0;
+        }
+        __syncthreads();
+        if (rot) {  // columns p, q of G (G R^H):  col_p' = cs col_p - conj(se) col_q,  col_q' = se col_p + cs col_q
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = tl + 16 * u;
+            const cplx x = Y[i * QSP_BIG_LDY + p], y = Y[i * QSP_BIG_LDY + q];
+            Y[i * QSP_BIG_LDY + p] = cmake(cs * x.x - (sx * y.x + sy * y.y), cs * x.y - (sx * y.y - sy * y.x));
+            Y[i * QSP_BIG_LDY + q] = cmake(cs * y.x + (sx * x.x - sy * x.y), cs * y.y + (sx * x.y + sy * x.x));
+          }
+        }
+        __syncthreads();
+      }
+      if (*rotflag == 0.0) break;
+      __syncthreads();
+    }
+    __syncthreads();
+    cplx* Jo2 = Jg + (long)task * QSP_BIG_PR * QSP_BIG_PR;
+    for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT)
+      Jo2[idx] = Y[(idx / QSP_BIG_PR) * QSP_BIG_LDY + QSP_BIG_PR + (idx % QSP_BIG_PR)];
+    return;
   }
 
   // ---- Cholesky G = L L^H: L is built in the right half of Y (one barrier per column: the trailing update reads the
