@@ -412,20 +412,32 @@ __global__ void __launch_bounds__(QSP_BIG_NT, 4) k_big_jac_solve(const BigJac* _
     }
   }
   __syncthreads();
-  // ---- convergence of this block pair: max |g_pq|^2 / (g_pp g_qq) ---------------------------
-  if (warp == 0) {
-    const double dp = Y[lane * QSP_BIG_LDY + lane].x;
-    sd[lane] = dp;
-    __syncwarp();
+  // ---- convergence of this block pair: max |g_pq|^2 / (g_pp g_qq), and the spread of the row norms --------------------
+  if (tid < QSP_BIG_PR) sd[tid] = Y[tid * QSP_BIG_LDY + tid].x;
+  __syncthreads();
+  {
     double mx = 0.0;
-    for (int q = 0; q < QSP_BIG_PR; ++q) {
-      if (q == lane) continue;
-      const double ab = dp * sd[q];
-      const double g2 = cabs2(Y[lane * QSP_BIG_LDY + q]);
-      if (ab > 1e-280) mx = fmax(mx, g2 / ab);
+    for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT) {
+      const int r = idx / QSP_BIG_PR, c = idx - r * QSP_BIG_PR;
+      const double ab = sd[r] * sd[c];
+      if (r != c && ab > 1e-280) mx = fmax(mx, cabs2(Y[r * QSP_BIG_LDY + c]) / ab);
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, shfl_xor_d(mx, o));
-    if (lane == 0) sd[32] = mx;
+    if (lane == 0) sd[40 + warp] = mx;
+    if (warp == 0) {
+      double dmax = sd[lane], dmin = sd[lane] > 0.0 ? sd[lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) {
+        dmax = fmax(dmax, shfl_xor_d(dmax, o));
+        dmin = fmin(dmin, shfl_xor_d(dmin, o));
+      }
+      if (lane == 0) sd[34] = (dmin >= 1e-8 * dmax) ? 1.0 : 0.0;  // well scaled: two-sided route below
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = sd[40];
+    for (int w = 1; w < QSP_BIG_NT / 32; ++w) mx = fmax(mx, sd[40 + w]);
+    sd[32] = mx;
   }
   __syncthreads();
   const double maxratio = sd[32];
@@ -444,15 +456,6 @@ __global__ void __launch_bounds__(QSP_BIG_NT, 4) k_big_jac_solve(const BigJac* _
   // plane rotations, so X <- J X stays an orthogonal transformation whatever rounding G accumulates, and convergence is
   // always judged on a freshly computed Gram matrix; only the RELATIVE accuracy of entries far below the largest one is
   // lost by updating G explicitly, which is why strongly graded (or rank deficient) panels take the Cholesky route. -------
-  if (warp == 0) {
-    double dmax = sd[lane], dmin = sd[lane] > 0.0 ? sd[lane] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) {
-      dmax = fmax(dmax, shfl_xor_d(dmax, o));
-      dmin = fmin(dmin, shfl_xor_d(dmin, o));
-    }
-    if (lane == 0) sd[34] = (dmin >= 1e-8 * dmax) ? 1.0 : 0.0;
-  }
-  __syncthreads();
   if (sd[34] != 0.0) {
     for (int idx = tid; idx < QSP_BIG_PR * QSP_BIG_PR; idx += QSP_BIG_NT) {
       const int i = idx / QSP_BIG_PR, k = idx - i * QSP_BIG_PR;
