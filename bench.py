@@ -144,8 +144,9 @@ def cpu_baseline(a, parity_npz=None):
         return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {str(e)[:200]}"}, par
     v = cores / wall
     return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} instances x all {a.layers} layers of {workload_name(a)} (numpy/scipy restatement of the "
-                      f"reference path, one single-threaded worker per host core, nproc = {cores}, {wall:.1f}s wall)"}, par
+            "sample": f"{cores} instances x [MPSPreparation.__init__ pipeline + all {a.layers} layers] of {workload_name(a)} "
+                      f"(numpy/scipy restatement of the reference path, one single-threaded worker per host core, "
+                      f"nproc = {cores}, {wall:.1f}s wall; the same work as the GPU arm's e2e figure)"}, par
 
 
 def run_reference(a):
@@ -159,7 +160,7 @@ def run_reference(a):
     walls = cpu_sample(a.L, a.chi, a.layers, cores, cores, reps=steps, workload=a.workload)
     t = float(np.mean(walls))
     v = cores / t
-    sample = (f"each step = {cores} instances x all {a.layers} layers of {workload_name(a)} on {cores} single-threaded "
+    sample = (f"each step = {cores} instances x [MPSPreparation.__init__ pipeline + all {a.layers} layers] of {workload_name(a)} on {cores} single-threaded "
               f"workers = every host core (nproc = {cores}; numpy/scipy restatement -- quimb, the reference's engine, "
               f"cannot be installed); MPS/s = instances / wall")
     world = int(os.environ.get("WORLD_SIZE", "1"))

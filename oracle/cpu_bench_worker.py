@@ -34,8 +34,9 @@ def one(args):
         raw = O.to_lpr(make_splitted_mps(make_aklt_mps(L // 2)[0]), "lrp")
     else:
         raw = O.random_mps(L, chi, seed)
-    t = O.prepare_target(raw, "lpr")
+    # timed like the GPU arm's end-to-end figure: MPSPreparation.__init__ (normalise + compress, tsp.py:63-77) and the call
     t0 = time.time()
+    t = O.prepare_target(raw, "lpr")
     O.sequential_unitary_circuit(t, layers, do_compression=True, max_bond_dim=chi, completion="lapack")
     return time.time() - t0
 
