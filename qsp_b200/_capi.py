@@ -63,7 +63,7 @@ _DEV_SIGNATURES = {
 
 EXPORTS = tuple(_SIGNATURES)
 DEV_EXPORTS = tuple(_DEV_SIGNATURES)
-DEV_LIB = os.path.join(_HERE, "libqsp_b200_dev.so")
+DEV_LIB = os.environ.get("QSP_B200_DEV_LIB") or os.path.join(_HERE, "libqsp_b200_dev.so")
 
 
 class QspError(RuntimeError):
