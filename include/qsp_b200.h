@@ -42,7 +42,7 @@ typedef struct {
 
 #define QSP_OK 0
 #define QSP_ERR_ARG 1         /* null pointer / non-positive size */
-#define QSP_ERR_UNSUPPORTED 2 /* bond dimension too large for this build's shared-memory kernels */
+#define QSP_ERR_UNSUPPORTED 2 /* shape not supported by this build (no bond-dimension limit since the batched large-bond path) */
 #define QSP_ERR_WORKSPACE 3   /* work_bytes smaller than the query says */
 #define QSP_ERR_CUDA 4        /* a launch failed; see qsp_last_cuda_error() */
 
@@ -63,7 +63,8 @@ long long qsp_launch_count(void);
 /* quimb MPS.left_canonize() in place (first half of `compress`, tsp.py:72, core.py:17,
  * sequential.py:54,57).  R has a non-negative real diagonal (quimb's stabilised QR).
  * Bonds whose (2D x D) site matrix fits shared memory (D <= ~85) need no workspace (the query
- * returns 0, work may be NULL); larger bonds (D <= 256) run out of an L2-resident scratch. */
+ * returns 0, work may be NULL); larger bonds (any size) take the batched blocked-Householder path
+ * (compact-WY panels, trailing updates and the thin Q as tensor-core GEMMs) out of the workspace. */
 size_t qsp_left_canonize_workspace_bytes(int B, int L, int D);
 int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_t* status, void* work,
                       size_t work_bytes, void* stream);
@@ -74,7 +75,10 @@ int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, int D, int32_
  * (right_canonize(normalize=True), sequential.py:53,56).  svals (optional): the nsv
  * largest singular values seen at each bond, svals[b][i-1][0..nsv) for the bond between
  * sites i-1 and i.  amp0 (optional): <0...0|out>/||out||, i.e. norm_mps_ovrlap(out,
- * cl_zero_mps(L)) (helper_routines.py:65-73, sequential.py:60). */
+ * cl_zero_mps(L)) (helper_routines.py:65-73, sequential.py:60).
+ * Site matrices up to 128 x 128 (bonds <= 64) stay on one SM for the whole sweep (register-resident Jacobi SVD); larger ones
+ * take batched launches per site: block one-sided Jacobi SVD on the FP64 tensor cores (DMMA) with TMA-staged panels and
+ * DMMA GEMMs -- that path reads one convergence flag per Jacobi sweep on the host (it synchronises `stream`). */
 size_t qsp_right_compress_workspace_bytes(int B, int L, int D_in, int D_out);
 int qsp_right_compress(const qsp_c128* in, const int32_t* bonds_in, int D_in, qsp_c128* out, int32_t* bonds_out,
                        int D_out, int B, int L, int max_bond, double cutoff, int normalize, double* svals, int nsv,

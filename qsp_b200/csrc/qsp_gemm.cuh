@@ -2,12 +2,11 @@
 //
 //   C[i*sCr + j*sCc]  (+)=  sum_k  opA(A[i*sAr + k*sAk]) * opB(B[k*sBk + j*sBc])
 //
-// All matrices on the hot path are small (<= 256 x 256) and live in L2 / shared memory,
-// so one CTA multiplies one instance's operands: operand tiles are staged through shared
-// memory (k-major, padded against bank conflicts), every thread owns a 4x4 register
-// micro-tile and issues 64 DFMA per 8 LDS.128.  tcgen05 has no FP64 kind; on B200 the
-// FP64 DMMA peak equals the DFMA peak, so the register-tiled DFMA loop is the right tool
-// ("why no tensor cores").
+// The matrices of the small-bond sweeps (<= 128 x 128) live in L2 / shared memory, so one CTA multiplies one
+// instance's operands.  Two variants: cta_zgemm_t (DFMA: k-major padded smem tiles, 4x4 register micro-tile per
+// thread, 64 DFMA per 8 LDS.128) and cta_zgemm_dmma_t (FP64 tensor cores, 8x8 complex tiles as four real DMMA
+// m8n8k4; used by the 256 / 512-thread sweeps).  tcgen05 has no FP64 kind and the DMMA peak equals the DFMA peak on
+// B200, so DMMA buys issue slots and operand bandwidth, not a higher ceiling.
 #pragma once
 #include "qsp_common.cuh"
 #include "qsp_mma.cuh"

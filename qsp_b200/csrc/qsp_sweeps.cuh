@@ -44,9 +44,6 @@ __host__ __device__ inline size_t lcanon_smem_bytes(int Dm, int nt) {
 // so a column is read and written once per reflector; the warp that finishes column j+1
 // immediately builds reflector j+1 (look-ahead), so there is one barrier per reflector.
 #define QSP_QR_MAXR 8
-// rows per lane of the large-bond variant (site matrix in the L2-resident scratch, 256 threads so that a column
-// and a reflector of 16 rows per lane fit the register file): 2*D <= 512
-#define QSP_QR_MAXR_BIG 16
 
 // reflector from column `col` (rows j..m-1): writes the scaled v below the diagonal, tau, beta.
 __device__ __forceinline__ void qr_make_reflector(cplx* col, int j, int m, int lane, cplx* tau, double* beta) {
@@ -159,19 +156,16 @@ template <int MAXR, bool SHARED>
 __device__ __noinline__ void cta_householder_qr_t(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
                                                   long long* pc);
 
-template <bool BIG>
 __device__ __forceinline__ void cta_householder_qr(cplx* S, int m, int n, int ldS, cplx* R, int ldR, cplx* tau, double* beta,
                                                    long long* pc) {
-  if (BIG && m > 32 * QSP_QR_MAXR)
-    cta_householder_qr_t<QSP_QR_MAXR_BIG, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
-  else if (m <= 32)
-    cta_householder_qr_t<1, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
+  if (m <= 32)
+    cta_householder_qr_t<1, true>(S, m, n, ldS, R, ldR, tau, beta, pc);
   else if (m <= 64)
-    cta_householder_qr_t<2, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
+    cta_householder_qr_t<2, true>(S, m, n, ldS, R, ldR, tau, beta, pc);
   else if (m <= 128)
-    cta_householder_qr_t<4, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
+    cta_householder_qr_t<4, true>(S, m, n, ldS, R, ldR, tau, beta, pc);
   else
-    cta_householder_qr_t<QSP_QR_MAXR, !BIG>(S, m, n, ldS, R, ldR, tau, beta, pc);
+    cta_householder_qr_t<QSP_QR_MAXR, true>(S, m, n, ldS, R, ldR, tau, beta, pc);
 }
 
 template <int MAXR, bool SHARED>
@@ -450,30 +444,15 @@ __device__ __noinline__ void cta_householder_qr_t(cplx* S, int m, int n, int ldS
   pc[3] += qsp_clock() - tck;
 }
 
-// gwork == null: S and R live in shared memory (lcanon_smem_bytes).  gwork != null (large bonds): they live in
-// a per-CTA slice of an L2-resident scratch (lcanon_work_elems each), shared memory holds tau/beta/GEMM tiles only
-// (lcanon_smem_bytes_big).
-__host__ __device__ inline long lcanon_work_elems(int Dm) { return (long)Dm * (2 * Dm + 1) + (long)Dm * Dm + 64; }
-__host__ __device__ inline size_t lcanon_smem_bytes_big(int Dm, int nt) {
-  return (size_t)Dm * (sizeof(cplx) + sizeof(double)) + 64 * sizeof(double) + qsp_gemm_smem_bytes(nt) + 64;
-}
-
-template <bool BIG>
+// S and R live in shared memory (lcanon_smem_bytes); bonds beyond that take big_left_canonize (qsp_big_sweeps.cuh).
 __device__ __forceinline__ void left_canon_impl(cplx* __restrict__ mps, int32_t* __restrict__ bonds, int B, int L, int D,
-                                                int Dm, int32_t* __restrict__ status, long long* prof, cplx* gwork) {
+                                                int Dm, int32_t* __restrict__ status, long long* prof) {
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   char* sm = QSP_SMEM_BASE();
   const int ldS = 2 * Dm + 1;
-  cplx *S, *R, *tau;
-  if (BIG) {
-    S = gwork + (long)blockIdx.x * lcanon_work_elems(Dm);
-    R = S + (size_t)Dm * ldS;
-    tau = (cplx*)sm;
-  } else {
-    S = (cplx*)sm;
-    R = S + (size_t)Dm * ldS;
-    tau = R + (size_t)Dm * Dm;
-  }
+  cplx* S = (cplx*)sm;
+  cplx* R = S + (size_t)Dm * ldS;
+  cplx* tau = R + (size_t)Dm * Dm;
   double* beta = (double*)(tau + Dm);
   double* red = beta + Dm;
   cplx* tiles = (cplx*)(((uintptr_t)(red + 64) + 15) & ~(uintptr_t)15);
@@ -519,7 +498,7 @@ __device__ __forceinline__ void left_canon_impl(cplx* __restrict__ mps, int32_t*
       }
       __syncthreads();
       pc[0] += qsp_clock() - tck;
-      cta_householder_qr<BIG>(S, m, n, ldS, R, Dm, tau, beta, pc);
+      cta_householder_qr(S, m, n, ldS, R, Dm, tau, beta, pc);
       tck = qsp_clock();
       pc[6] += 1;
       const int K = imin(m, n);
@@ -545,7 +524,7 @@ __device__ __forceinline__ void left_canon_impl(cplx* __restrict__ mps, int32_t*
 
 __global__ void __launch_bounds__(512) k_left_canon(cplx* __restrict__ mps, int32_t* __restrict__ bonds, int B, int L, int D,
                                                     int Dm, int32_t* __restrict__ status, long long* prof) {
-  left_canon_impl<false>(mps, bonds, B, L, D, Dm, status, prof, nullptr);
+  left_canon_impl(mps, bonds, B, L, D, Dm, status, prof);
 }
 // ----------------------------------------------------------------------------------
 // right compression (truncating SVD sweep) of a left-canonical MPS
