@@ -7,6 +7,7 @@ live bond extents in `bonds[B, L+1]` int32; element (l, p, r) of a site is mps[b
 import concurrent.futures
 import contextlib
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -15,6 +16,7 @@ from . import _runtime
 from ._capi import FLAG_NO_ENCODED, FLAG_SECOND_PASS, QspError
 
 CUTOFF = 1e-10  # quimb's default relative cutoff used throughout the reference path
+NSIDE = int(os.environ.get("QSP_B200_STREAMS", "2"))  # streams (and workspaces) the chunks of one batch alternate between
 
 
 def _p(t):
@@ -241,8 +243,8 @@ class Engine:
         two = len(starts) > 1 and overlap_chunks
         if two:
             if self._side is None:
-                self._side = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-                self._side_work = [None, None]
+                self._side = [torch.cuda.Stream(dev) for _ in range(NSIDE)]
+                self._side_work = [None] * NSIDE
             ev0 = torch.cuda.Event()
             ev0.record(cur)
             for s_ in self._side:
@@ -253,7 +255,7 @@ class Engine:
             nb = self.seq_workspace_bytes(n, L, D, layers, max_bond, flags)
             whole = n == B
             if two:
-                k = ci % 2
+                k = ci % NSIDE
                 if self._side_work[k] is None or self._side_work[k].numel() < nb:
                     self._side_work[k] = None
                     self._side_work[k] = torch.empty(int(nb), dtype=torch.uint8, device=dev)
@@ -286,11 +288,11 @@ class Engine:
             def worker(k):
                 torch.cuda.set_device(dev)
                 for ci, b0 in enumerate(starts):
-                    if ci % 2 == k:
+                    if ci % NSIDE == k:
                         run_chunk(ci, b0)
 
-            with concurrent.futures.ThreadPoolExecutor(2) as ex:
-                for f in [ex.submit(worker, 0), ex.submit(worker, 1)]:
+            with concurrent.futures.ThreadPoolExecutor(NSIDE) as ex:
+                for f in [ex.submit(worker, k) for k in range(NSIDE)]:
                     f.result()
         else:
             for ci, b0 in enumerate(starts):

@@ -304,6 +304,28 @@ def test_overlapped_chunks_match_single_call(drv):
     assert torch.equal(torch.view_as_real(out["dis_overlaps"]), torch.view_as_real(one.dis_overlaps.cpu()))
 
 
+def test_overlapped_chunks_large_bonds(drv):
+    """bonds > 64: the chunks of a batch run on two streams fed by two host threads (the large-bond sweeps synchronise their
+    stream once per Jacobi sweep); same results as one call up to rounding (the column splits of the Gram launches, and with
+    them the summation order, depend on the chunk size)"""
+    import torch
+
+    from bench import synth_batch
+    from qsp_b200.engine import Engine
+
+    eng = Engine()
+    B, L, chi, layers = 6, 14, 70, 2
+    raw, bonds = synth_batch(torch, B, L, chi, eng.device, 9)
+    assert int(eng.prepare_target(raw, bonds).max()) == 0
+    one = eng.seq_prepare(raw, bonds, layers, max_bond=chi)
+    many = eng.seq_prepare(raw, bonds, layers, max_bond=chi, chunk=2)
+    torch.cuda.synchronize()
+    assert int(one.status.max()) == 0 and int(many.status.max()) == 0
+    assert float((one.dis_overlaps - many.dis_overlaps).abs().max()) < 1e-12
+    assert float((one.overlaps[layers - 1] - many.overlaps[layers - 1]).abs().max()) < 1e-12
+    assert float((one.d2_svals - many.d2_svals).abs().max()) < 1e-12 and torch.equal(one.kind, many.kind)
+
+
 def test_batched_circuits_and_statevector_check(drv):
     """(overlap, circ) for a batch: circuits are materialised on demand from the device-resident gates, and the
     reference's statevector cross-check (qiskit_circuit.py:52-67) runs on the device for all instances at 18 qubits
