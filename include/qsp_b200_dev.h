@@ -17,6 +17,7 @@ extern "C" {
  * multiple of 32), nt threads per CTA. */
 int qsp_jacobi_bench_fat(qsp_c128* W, int nrows, int ldw, int B, int* sweeps, int* ok, void* stream);
 int qsp_smem_probe(double* out, int blocks, int iters, int mode, void* stream); /* shared-memory bandwidth probe */
+int qsp_tmem_probe(double* out, int blocks, int iters, int mode, void* stream); /* tensor-memory (tcgen05.ld/st) bandwidth probe */
 void qsp_jacobi_variant(int bits); /* timing experiments: disables parts of the Jacobi round (results invalid) */
 void qsp_debug_flags(int flags);    /* test hook: bit 0 = take the large-bond left-canonise path at any size */
 int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int nt, int* sweeps, int* ok, void* stream);

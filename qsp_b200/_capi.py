@@ -51,6 +51,7 @@ _DEV_SIGNATURES = {
     "qsp_debug_flags": (None, [_i]),
     "qsp_jacobi_bench_fat": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "qsp_smem_probe": (_i, [_p, _i, _i, _i, _p]),
+    "qsp_tmem_probe": (_i, [_p, _i, _i, _i, _p]),
     "qsp_jacobi_variant": (None, [_i]),
     "qsp_jacobi_bench": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "qsp_dfma_probe": (_i, [_p, _i, _i, _i, _p]),

@@ -70,19 +70,37 @@ extern "C" int qsp_dmma_probe(double* out, int blocks, int threads, int iters, v
 // nrows x ldw matrix (W[B][nrows][ldw]) in place; sweeps[B] receives the sweep counts.
 template <int NTMAX>
 __global__ void __launch_bounds__(NTMAX) k_jacobi_bench(cplx* W, int nrows, int ndotp, int ldw, int B, int cap_elems,
-                                                        int* sweeps, int* ok) {
+                                                        int* sweeps, int* ok, int use_tmem) {
   char* sm = QSP_SMEM_BASE();
   cplx* Wsm = (cplx*)sm;
   double* red = (double*)(sm + (size_t)cap_elems * sizeof(cplx));
+  uint32_t* tslot = (uint32_t*)(red + 58);
+  use_tmem = use_tmem && blockDim.x == 512;
+  if (use_tmem && (threadIdx.x >> 5) == 0) tmem_alloc<256>(tslot);
+  tmem_fence_before();
+  __syncthreads();
+  tmem_fence_after();
+  JacobiIO io;
+  io.src = nullptr;
+  io.src_ld = io.src_cols = 0;
+  io.norms_off = -1;
+  io.norms_done = false;
+  io.tmem = use_tmem ? *tslot : 0u;
+  io.tmem_ok = use_tmem != 0;
   for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
     int ns = 0;
     const double tol = 4e-16 * sqrt((double)ndotp);
-    bool c = jacobi_svd_rows(W + (long)inst * nrows * ldw, nrows, ndotp, ldw, Wsm, cap_elems, 8, tol * tol, 60, red, &ns);
+    bool c = jacobi_svd_rows(W + (long)inst * nrows * ldw, nrows, ndotp, ldw, Wsm, cap_elems, 8, tol * tol, 60, red, &ns, &io);
     if (threadIdx.x == 0) {
       sweeps[inst] = ns;
       ok[inst] = c ? 1 : 0;
     }
     __syncthreads();
+  }
+  if (use_tmem) {
+    tmem_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc<256>(io.tmem);
   }
 }
 // Experiment: "fat thread" geometry -- 256 threads, teams of 4 lanes, 32 columns per lane (row half
@@ -154,6 +172,79 @@ extern "C" int qsp_smem_probe(double* out, int blocks, int iters, int mode, void
   ++g_launches;
   return check_launch();
 }
+// Tensor-memory bandwidth probe with the Jacobi access pattern: every thread moves 16 complex128 (64 columns of its
+// TMEM lane) per iteration, two per instruction.  mode 0 = load only (wait per chunk), 1 = store only,
+// 2 = load + store, 3 = load only with one wait per 16 elements.  out[0] = cycles per iteration (block 0).
+#include "qsp_tmem.cuh"
+__global__ void __launch_bounds__(512) k_tmem_probe(double* out, int iters, int mode) {
+#ifndef QSP_EMU
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<256>(&tslot);
+  tmem_fence_before();
+  __syncthreads();
+  tmem_fence_after();
+  const uint32_t base = tslot;
+  const uint32_t mine = base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+  cplx R[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) R[j] = cmake(j, tid);
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) tmem_st2(mine + 4 * j, R[j], R[j + 1]);
+  tmem_wait_st();
+  tmem_fence_before();
+  __syncthreads();
+  tmem_fence_after();
+  cplx acc = cmake(0, 0);
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        cplx a, b;
+        tmem_ld2(mine + 4 * j, a, b);
+        tmem_wait_ld();
+        acc = cadd(acc, cadd(a, b));
+      }
+    } else if (mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) tmem_st2(mine + 4 * j, R[j], R[j + 1]);
+      tmem_wait_st();
+    } else if (mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        cplx a, b;
+        tmem_ld2(mine + 4 * j, a, b);
+        tmem_wait_ld();
+        tmem_st2(mine + 4 * j, R[j], R[j + 1]);
+        R[j] = a;
+        R[j + 1] = b;
+      }
+      tmem_wait_st();
+    } else {
+      cplx a[16];
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) tmem_ld2(mine + 4 * j, a[j], a[j + 1]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc = cadd(acc, a[j]);
+    }
+  }
+  const long long t1 = clock64();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc = cadd(acc, R[j]);
+  if (acc.x == 1.2345e300) out[1] = acc.y;
+  if (blockIdx.x == 0 && tid == 0) out[0] = (double)(t1 - t0) / iters;
+  tmem_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(base);
+#endif
+}
+extern "C" int qsp_tmem_probe(double* out, int blocks, int iters, int mode, void* stream) {
+  QSP_LAUNCH(k_tmem_probe, blocks, 512, 0, (qsp_stream_t)stream, out, iters, mode);
+  ++g_launches;
+  return check_launch();
+}
 extern "C" void qsp_jacobi_variant(int v) {
 #ifdef QSP_JACOBI_ABLATION
   cudaMemcpyToSymbol(g_jvar, &v, sizeof(int));
@@ -172,11 +263,11 @@ extern "C" int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int 
   if (nt > 512) {
     QSP_PREP_KERNEL(k_jacobi_bench<1024>, smem);
     QSP_LAUNCH(k_jacobi_bench<1024>, grid, nt, smem, (qsp_stream_t)stream, (cplx*)W, nrows, ndotp, ldw, B, (int)cap, sweeps,
-               ok);
+               ok, 0);
   } else {
     QSP_PREP_KERNEL(k_jacobi_bench<512>, smem);
     QSP_LAUNCH(k_jacobi_bench<512>, grid, nt, smem, (qsp_stream_t)stream, (cplx*)W, nrows, ndotp, ldw, B, (int)cap, sweeps,
-               ok);
+               ok, g_tmem);
   }
   ++g_launches;
   return check_launch();

@@ -244,17 +244,25 @@ __host__ __device__ inline bool jacobi_oe_geometry(int nt, int nrows, int ldw, i
 }
 
 // rotation parameters from the Gram entries: x' = cs x - se y, y' = conj(se) x + cs y
-// with se = s e^{i phi}.  One sqrt, one reciprocal, one rsqrt (no division by |g|).
+// with se = s e^{i phi}.  With d = beta - alpha, h = sqrt(d^2 + 4|g|^2), u = h + |d|:
+//   cs = sqrt(u / 2h) = (u/2) sw,   s e^{i phi} = sign(d) sw g,   sw = rsqrt(h u / 2)   (cs^2 + s^2 = 1 identically)
+// -- two reciprocal square roots and no division or square root on the dependent chain of a round
+// (h = q rsqrt(q)); the tangent, where needed, is t e^{i phi} = w g with w = sign(d) 2/u = sign(d) sw^2 h.
+__device__ __forceinline__ void jacobi_rotation_sw(double d, double g2, double& cs, double& sws, double& h) {
+  const double q = fma(d, d, 4.0 * g2);
+  h = q * qsp_rsqrt(q);
+  const double u = h + fabs(d);
+  const double sw = qsp_rsqrt(0.5 * h * u);
+  const bool tiny = !(q > 1e-290);  // both rows ~1e-70 and below (q under/near the denormals): leave them alone
+  cs = tiny ? 1.0 : 0.5 * u * sw;
+  sws = tiny ? 0.0 : (d >= 0.0 ? sw : -sw);
+}
 __device__ __forceinline__ void jacobi_rotation(double al, double be, double gx, double gy, double g2, double& cs,
                                                 double& sx, double& sy) {
-  const double d = be - al;
-  const double h = sqrt(fma(d, d, 4.0 * g2));
-  const double w = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);  // t e^{i phi} = w g
-  const double t2 = w * w * g2;
-  cs = qsp_rsqrt(1.0 + t2);
-  const double cw = cs * w;
-  sx = cw * gx;
-  sy = cw * gy;
+  double sws, h;
+  jacobi_rotation_sw(be - al, g2, cs, sws, h);
+  sx = sws * gx;
+  sy = sws * gy;
 }
 
 // TPPC > 0 fixes the team width at compile time and FULL asserts jdot == jlen == CPL (no column
@@ -275,11 +283,15 @@ __device__ __forceinline__ void jacobi_rotation(double al, double be, double gx,
 //              the orthogonalised rows are still written to Wg
 //   norms_off  shared-memory offset of a double[nrows] that receives the SQUARED row norms over the Gram columns
 //              (< 0: none); norms_done is set when they were written
+//   tmem       base address of >= 192 allocated tensor-memory columns (tmem_ok set): the 128 x 128 problem keeps
+//              48 of its 64 shared rows there (jacobi_rows_oe_tmem)
 struct JacobiIO {
   const cplx* src;
   int src_ld, src_cols;
   int norms_off;
   bool norms_done;
+  uint32_t tmem;
+  bool tmem_ok;
 };
 
 template <int CPL, int NP, bool HOLD, int TPPC = 0, bool FULL = false, int FASTSEL = -1>
@@ -397,12 +409,11 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
             // true Gram entries: alpha = ds^2 al, beta = dr^2 be, |g|^2 = ds^2 dr^2 |g~|^2
             const double ds2 = FAST ? ds * ds : 1.0, dr2 = FAST ? dr[q] * dr[q] : 1.0;
             const double A = ds2 * al, Bq = dr2 * be, g2 = ds2 * dr2 * g2t;
-            const double d = Bq - A;
-            const double h = sqrt(fma(d, d, 4.0 * g2));
-            const double w = (d >= 0.0 ? 2.0 : -2.0) / (fabs(d) + h);  // t e^{i phi} = w g
-            const double cs = qsp_rsqrt(fma(w * w, g2, 1.0));
-            // FAST: tau1 = w dr^2 g~, tau2 = w ds^2 conj(g~) = (t2x, -t2y);  plain: s e^{i phi} = c w g
-            const double w1 = FAST ? w * dr2 : cs * w, w2 = FAST ? w * ds2 : cs * w;
+            double cs, sws, h;
+            jacobi_rotation_sw(Bq - A, g2, cs, sws, h);
+            // FAST: tau1 = w dr^2 g~, tau2 = w ds^2 conj(g~) = (t2x, -t2y), w = sws sw h;  plain: s e^{i phi} = sws g
+            const double wt = FAST ? sws * fabs(sws) * h : sws;
+            const double w1 = FAST ? wt * dr2 : wt, w2 = FAST ? wt * ds2 : wt;
             const double t1x = w1 * gx, t1y = w1 * gy;
             const double t2x = w2 * gx, t2y = w2 * gy;
             const double c0 = FAST ? 1.0 : cs;  // plain rotations scale the kept term by c
@@ -533,6 +544,253 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
   return conv;
 }
 
+#ifdef QSP_DEV_BUILD
+// ----------------------------------------------------------------------------------
+// EXPERIMENT (development build only, scripts/jacobi_bench.py with QSP_DEBUG_FLAGS=2; profiles/r2_tmem_jacobi.md):
+// the 128 x 128 problem (bulk sites of the chi = 64 layer loop) with three quarters of the shared rows in
+// TENSOR MEMORY.  The round of jacobi_rows_oe is bound by its three shared-memory passes over the 64 rows at
+// even positions (3 x 128 KB at ~125 B/clk, profiles/r1_ncu_right_compress.md); tcgen05.ld / tcgen05.st move
+// the same bytes at ~300 B/clk on a pipe of their own (scripts/tmem_probe.py), but a thread only reaches its own
+// TMEM lane, and only warps w, w+4, w+8, w+12 share a quadrant.  So the chain of teams is threaded through the
+// CTA such that neighbours sit on the SAME lanes of the same quadrant in consecutive warps:
+//     chain position p = ((quadrant * 4 + lane group) * 4 + warp / 4)
+// and the row that teams p-1 and p hand back and forth (slot p) lives in the TMEM lanes they share when
+// p % 4 != 0 (48 slots, 64 columns each) and in shared memory where the chain changes lanes (16 slots, 32 KB).
+// Same arithmetic, ordering and convergence rule as jacobi_rows_oe<16, 1, false, 8, true>.
+#include "qsp_tmem.cuh"
+// timing ablations of the round loop (results invalid when set; development builds only)
+#ifdef QSP_TJ_NOWAITLD
+#define QSP_TJ_WAIT_LD()
+#else
+#define QSP_TJ_WAIT_LD() tmem_wait_ld()
+#endif
+#ifdef QSP_TJ_NOWAITST
+#define QSP_TJ_WAIT_ST()
+#else
+#define QSP_TJ_WAIT_ST() tmem_wait_st()
+#endif
+#ifdef QSP_TJ_NOFENCE
+#define QSP_TJ_FENCE_B()
+#define QSP_TJ_FENCE_A()
+#else
+#define QSP_TJ_FENCE_B() tmem_fence_before()
+#define QSP_TJ_FENCE_A() tmem_fence_after()
+#endif
+__device__ __noinline__ bool jacobi_rows_oe_tmem(cplx* Wg, int s_off, double tol2, int max_sweeps, int red_off,
+                                                 int* sweeps_out, JacobiIO* io) {
+  constexpr int CPL = 16, TPP = 8, NR = 128, LDW = 128, NSLOT = 64;
+  cplx* S = (cplx*)(QSP_SMEM_BASE() + s_off);
+  double* red = (double*)(QSP_SMEM_BASE() + red_off);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int grp = lane >> 3, tl = lane & 7, quad = warp & 3, jj = warp >> 2;
+  const int p = (quad * 4 + grp) * 4 + jj;  // chain position: register row 2p+1, own slot p
+  const uint32_t tq = io->tmem + ((uint32_t)(quad * 32) << 16);
+  cplx R[CPL];
+  {
+    const bool ext = io->src != nullptr;
+    const cplx* src = ext ? io->src : Wg;
+    const long sld = ext ? io->src_ld : LDW;
+    const int scols = ext ? io->src_cols : LDW;
+    const cplx* ro = src + (long)(2 * p + 1) * sld;
+    const cplx* re = src + (long)(2 * p) * sld;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) R[j] = (tl + j * TPP < scols) ? ro[tl + j * TPP] : cmake(0.0, 0.0);
+    if (jj == 0) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) S[(p >> 2) * LDW + tl + j * TPP] = (tl + j * TPP < scols) ? re[tl + j * TPP] : cmake(0.0, 0.0);
+    } else {
+      const uint32_t ta = tq + (uint32_t)((jj - 1) * 64);
+#pragma unroll
+      for (int j = 0; j < CPL; j += 2) {
+        const cplx a = (tl + j * TPP < scols) ? re[tl + j * TPP] : cmake(0.0, 0.0);
+        const cplx b = (tl + (j + 1) * TPP < scols) ? re[tl + (j + 1) * TPP] : cmake(0.0, 0.0);
+        tmem_st2(ta + 4 * j, a, b);
+      }
+      tmem_wait_st();
+    }
+  }
+  tmem_fence_before();
+  __syncthreads();
+  tmem_fence_after();
+  bool conv = false;
+  int sweeps = 0;
+  volatile int* flag = (volatile int*)(red + 48);  // set when a rotation above QSP_JAC_QUAD happened
+  while (sweeps < max_sweeps) {
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+    for (int r = 0; r < NR; ++r) {
+      const int odd = r & 1;
+      const int slot = p + odd;
+      const bool in_tmem = odd ? (jj != 3) : (jj != 0);  // warp uniform
+      const bool valid = slot < NSLOT;  // only the last team idles, in the odd rounds (a shared-memory warp)
+      const uint32_t ta = tq + (uint32_t)((odd ? jj : jj - 1) * 64);
+      cplx* xs = S + ((valid ? slot : 0) >> 2) * LDW + tl;
+      // one instruction stream for both homes of the partner row; the chunk after the current one is in flight
+      // while the current one is consumed (tcgen05.wait::ld waits for everything outstanding)
+      cplx xa, xb;
+#ifdef QSP_TJ_NOTMEM
+#define QSP_TJ_LD2(a, x, y) (x = R[0], y = R[1])
+#define QSP_TJ_ST2(a, x, y)
+#else
+#define QSP_TJ_LD2(a, x, y) tmem_ld2(a, x, y)
+#define QSP_TJ_ST2(a, x, y) tmem_st2(a, x, y)
+#endif
+#define QSP_TJ_LOAD(j)                    \
+  if (in_tmem) {                          \
+    QSP_TJ_LD2(ta + 4 * (j), xa, xb);     \
+  } else {                                \
+    xa = xs[(j) * TPP];                   \
+    xb = xs[((j) + 1) * TPP];             \
+  }
+      double al = 0.0, be = 0.0, gx = 0.0, gy = 0.0;
+      QSP_TJ_LOAD(0);
+#pragma unroll
+      for (int j0 = 0; j0 < CPL; j0 += 2) {
+        if (in_tmem) QSP_TJ_WAIT_LD();
+        const cplx xt[2] = {xa, xb};
+        if (j0 + 2 < CPL) { QSP_TJ_LOAD(j0 + 2); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const cplx y = R[j0 + u];
+          const cplx xv = xt[u];
+          al = fma(xv.x, xv.x, al);
+          al = fma(xv.y, xv.y, al);
+          be = fma(y.x, y.x, be);
+          be = fma(y.y, y.y, be);
+          gx = fma(xv.x, y.x, gx);
+          gx = fma(xv.y, y.y, gx);
+          gy = fma(xv.y, y.x, gy);
+          gy = fma(-xv.x, y.y, gy);
+        }
+      }
+#pragma unroll
+      for (int o = TPP >> 1; o > 0; o >>= 1) {
+        al += shfl_xor_d(al, o);
+        be += shfl_xor_d(be, o);
+        gx += shfl_xor_d(gx, o);
+        gy += shfl_xor_d(gy, o);
+      }
+      const double g2 = gx * gx + gy * gy, ab = al * be;
+      const bool rot = valid && ab > 1e-280 && g2 > tol2 * ab;
+      if (__any_sync(QSP_FULL_MASK, rot || !valid)) {
+        // branch free (tcgen05.ld / st are warp-aligned: no divergence may reach them); teams that do not rotate
+        // take the identity, i.e. their rows just trade places
+        double cs, sws, h;
+        jacobi_rotation_sw(be - al, g2, cs, sws, h);
+        cs = rot ? cs : 1.0;
+        sws = rot ? sws : 0.0;
+        if (rot && tl == 0 && g2 > (QSP_JAC_QUAD * QSP_JAC_QUAD) * ab) *flag = 1;
+        __syncwarp();
+        double tx = sws * gx, ty = sws * gy;  // s e^{i phi}
+        if (!valid) cs = 0.0, tx = -1.0, ty = 0.0;  // the idle team keeps its register row: x' = y (nothing is stored)
+        QSP_TJ_LOAD(0);
+#pragma unroll
+        for (int j0 = 0; j0 < CPL; j0 += 2) {
+          if (in_tmem) QSP_TJ_WAIT_LD();
+          const cplx xt[2] = {xa, xb};
+          if (j0 + 2 < CPL) { QSP_TJ_LOAD(j0 + 2); }
+          cplx yn[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const cplx y = R[j0 + u];
+            const cplx xv = xt[u];
+            cplx xn;
+            xn.x = fma(-tx, y.x, fma(ty, y.y, cs * xv.x));
+            xn.y = fma(-tx, y.y, fma(-ty, y.x, cs * xv.y));
+            yn[u].x = fma(tx, xv.x, fma(ty, xv.y, cs * y.x));
+            yn[u].y = fma(tx, xv.y, fma(-ty, xv.x, cs * y.y));
+            R[j0 + u] = xn;
+          }
+          if (in_tmem) {  // the rows trade places
+            QSP_TJ_ST2(ta + 4 * j0, yn[0], yn[1]);
+          } else if (valid) {
+            xs[j0 * TPP] = yn[0];
+            xs[(j0 + 1) * TPP] = yn[1];
+          }
+        }
+      } else {
+        QSP_TJ_LOAD(0);
+#pragma unroll
+        for (int j0 = 0; j0 < CPL; j0 += 2) {
+          if (in_tmem) QSP_TJ_WAIT_LD();
+          const cplx xt[2] = {xa, xb};
+          if (j0 + 2 < CPL) { QSP_TJ_LOAD(j0 + 2); }
+          if (in_tmem) {
+            QSP_TJ_ST2(ta + 4 * j0, R[j0], R[j0 + 1]);
+          } else if (valid) {
+            xs[j0 * TPP] = R[j0];
+            xs[(j0 + 1) * TPP] = R[j0 + 1];
+          }
+          R[j0] = xt[0];  // (every team of the warp is valid on this path)
+          R[j0 + 1] = xt[1];
+        }
+      }
+#undef QSP_TJ_LOAD
+      if (in_tmem) QSP_TJ_WAIT_ST();
+      QSP_TJ_FENCE_B();
+      __syncthreads();
+      QSP_TJ_FENCE_A();
+    }
+    ++sweeps;
+    if (*flag == 0) {  // (ordered by the barrier above)
+      conv = true;
+      break;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  // rows out (a sweep has an even number of rounds: every team is back on its own slot) + squared norms
+  double n_odd = 0.0, n_even = 0.0;
+  {
+    cplx* wo = Wg + (long)(2 * p + 1) * LDW;
+    cplx* we = Wg + (long)(2 * p) * LDW;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      wo[tl + j * TPP] = R[j];
+      n_odd = fma(R[j].x, R[j].x, fma(R[j].y, R[j].y, n_odd));
+    }
+    if (jj == 0) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const cplx v = S[(p >> 2) * LDW + tl + j * TPP];
+        we[tl + j * TPP] = v;
+        n_even = fma(v.x, v.x, fma(v.y, v.y, n_even));
+      }
+    } else {
+      const uint32_t ta = tq + (uint32_t)((jj - 1) * 64);
+#pragma unroll
+      for (int j = 0; j < CPL; j += 2) {
+        cplx a, b;
+        tmem_ld2(ta + 4 * j, a, b);
+        tmem_wait_ld();
+        we[tl + j * TPP] = a;
+        we[tl + (j + 1) * TPP] = b;
+        n_even = fma(a.x, a.x, fma(a.y, a.y, n_even));
+        n_even = fma(b.x, b.x, fma(b.y, b.y, n_even));
+      }
+    }
+  }
+  if (io->norms_off >= 0) {
+    double* nrm = (double*)(QSP_SMEM_BASE() + io->norms_off);
+#pragma unroll
+    for (int o = TPP >> 1; o > 0; o >>= 1) {
+      n_odd += shfl_xor_d(n_odd, o);
+      n_even += shfl_xor_d(n_even, o);
+    }
+    if (tl == 0) {
+      nrm[2 * p + 1] = n_odd;
+      nrm[2 * p] = n_even;
+    }
+    io->norms_done = true;
+  }
+  tmem_fence_before();
+  __syncthreads();
+  tmem_fence_after();
+  if (sweeps_out) *sweeps_out = sweeps;
+  return conv;
+}
+#endif  // QSP_DEV_BUILD
+
 // Can the register-resident path take an (nrows x ldw) problem?  (ldw already padded)
 __host__ __device__ inline bool jacobi_oe_fits(int nt, int nrows, int ldw, int cap_elems) {
   int tpp, np;
@@ -564,6 +822,10 @@ __device__ inline bool jacobi_svd_rows(cplx* Wg, int nrows, int ndotp, int ldw, 
                                                                        r_off, sweeps_out, io)
     if (np == 1 && jdot == jlen) {  // power-of-two problems of the layer loop and of the input pipeline
       if (tpp == 8) {
+#ifdef QSP_DEV_BUILD
+        if (jlen == 16 && nrows == 128 && nt == 512 && io && io->tmem_ok)  // experiment: rows in tensor memory
+          return jacobi_rows_oe_tmem(Wg, s_off, tol2, max_sweeps, r_off, sweeps_out, io);
+#endif
         if (jlen == 16) return QSP_OEF(16, false, 8);  // 128 x 128 (chi = 64 bulk)
         if (jlen == 8) return QSP_OEF(8, true, 8);     // 64 x 64 (chi = 32)
         if (jlen == 4) return QSP_OEF(4, true, 8);     // 32 x 32 (chi = 16)

@@ -779,6 +779,8 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       io.src_ld = io.src_cols = 0;
       io.norms_off = (int)((char*)norms - sm);
       io.norms_done = false;
+      io.tmem = 0u;
+      io.tmem_ok = false;
       if (oe && !modeC) {
         // the register path loads M itself (zero padded on the fly) and leaves s Vh in Wg: no staging copy
         io.src = Mg;

@@ -8,6 +8,8 @@ B = int(sys.argv[4]) if len(sys.argv) > 4 else 148
 var = int(os.environ.get("JVAR", "0"))
 lib = _runtime.dev_lib(); dev = torch.device("cuda:0")
 lib.qsp_jacobi_variant(var)
+if os.environ.get('QSP_DEBUG_FLAGS'):  # bit 1: rows of the 128 x 128 problem in tensor memory (experiment)
+    lib.qsp_debug_flags(int(os.environ['QSP_DEBUG_FLAGS'], 0))
 g = torch.Generator(device=dev); g.manual_seed(0)
 W0 = torch.complex(torch.randn((B, nrows, ldw), generator=g, device=dev, dtype=torch.float64),
                    torch.randn((B, nrows, ldw), generator=g, device=dev, dtype=torch.float64))

@@ -51,6 +51,7 @@ struct Block {
   Group named[16];
   std::vector<Group> warp_bar;
   std::vector<double> xchg, xchg2;  // 32 doubles per warp each
+  std::vector<uint32_t> tmem;       // tensor memory: 128 lanes x 512 columns (allocated on first use)
   std::function<void()> body;
   unsigned nthreads = 0;
   int cur = -1;
@@ -148,6 +149,27 @@ inline double __shfl_xor_sync(unsigned m, double v, int mask, int width = 32) {
 }
 inline int __shfl_sync(unsigned m, int v, int src, int width = 32) {
   return (int)__shfl_sync(m, (double)v, src, width);
+}
+inline int __any_sync(unsigned, int pred) {
+  emu::Block* b = emu::g_blk;
+  unsigned t = emu::g_threadIdx.x, w = t / 32;
+  b->xchg[t] = pred ? 1.0 : 0.0;
+  emu::group_sync(b->warp_bar[w], 32);
+  int r = 0;
+  for (unsigned l = 0; l < 32; ++l) r |= (b->xchg[w * 32 + l] != 0.0);
+  emu::group_sync(b->warp_bar[w], 32);
+  return r;
+}
+// tensor memory cell of the calling thread (lane 32 (warp % 4) + lane of the warp), column `col`
+inline uint32_t* emu_tmem_cell(unsigned col) {
+  emu::Block* b = emu::g_blk;
+  if (b->tmem.empty()) b->tmem.assign(128 * 512, 0u);
+  const unsigned t = emu::g_threadIdx.x, lane = 32 * ((t / 32) % 4) + t % 32;
+  if (col >= 512) {
+    fprintf(stderr, "emu: tensor-memory column %u out of range\n", col);
+    abort();
+  }
+  return &b->tmem[lane * 512 + col];
 }
 inline int __shfl_xor_sync(unsigned m, int v, int mask, int width = 32) {
   return (int)__shfl_xor_sync(m, (double)v, mask, width);

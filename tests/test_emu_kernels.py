@@ -112,11 +112,14 @@ def _jacobi_cases(nrows, ncols, seed=3):
     return {"full": full, "rank3": low, "graded": graded, "duplicates": dup, "zero_row": zero, "clustered": clustered}
 
 
-@pytest.mark.parametrize("nrows,ldw,nt", [(16, 128, 64), (15, 128, 64), (8, 64, 64)])
+@pytest.mark.parametrize("nrows,ldw,nt", [(16, 128, 64), (15, 128, 64), (8, 64, 64), (128, 128, 512)])
 def test_jacobi_register_variants(drv, nrows, ldw, nt):
     """the register-resident odd-even Jacobi on its own: (16,128,64) is the 16-columns-per-lane geometry of the
-    headline shape (plain rotations, carried row norms); singular values to 1e-12, rows orthogonal."""
+    headline shape (plain rotations, carried row norms); (128,128,512) is the headline problem itself, which keeps 48 of
+    its 64 shared rows in (emulated) tensor memory; singular values to 1e-12, rows orthogonal."""
     cases = _jacobi_cases(nrows, ldw)
+    if nrows >= 128:  # (emulation time: 512 fibers)
+        cases = {k: cases[k] for k in ("full", "clustered")}
     W = np.ascontiguousarray(np.stack(list(cases.values())))
     B = W.shape[0]
     ref = W.copy()
@@ -126,10 +129,15 @@ def test_jacobi_register_variants(drv, nrows, ldw, nt):
     for k, name in enumerate(cases):
         s_ref = np.linalg.svd(ref[k], compute_uv=False)
         s = np.sort(np.linalg.norm(W[k], axis=1))[::-1]
-        assert np.allclose(s, s_ref, rtol=1e-12, atol=1e-13 * s_ref[0]), name
+        # 64 singular values inside a relative window of 6e-8: the quadratic-convergence stop (largest rotation of the
+        # last sweep below 3e-8) leaves ~1e-11 there, the same in the shared-memory and the tensor-memory variant
+        rtol = 1e-10 if (name == "clustered" and nrows >= 128) else 1e-12
+        assert np.allclose(s, s_ref, rtol=rtol, atol=1e-13 * s_ref[0]), name
         keep = np.linalg.norm(W[k], axis=1) > 1e-8 * s_ref[0]
         V = W[k][keep] / np.linalg.norm(W[k][keep], axis=1)[:, None]
-        assert np.abs(V @ V.conj().T - np.eye(keep.sum())).max() < 1e-13, name
+        # (the same 64-fold cluster: every rotation inside it is a large-angle one however small the Gram entry, so the
+        # last sweep's rotations leave ~1e-9 between its members; multiplets of a few states are not affected)
+        assert np.abs(V @ V.conj().T - np.eye(keep.sum())).max() < (1e-8 if (name == "clustered" and nrows >= 128) else 1e-13), name
         # the rotations are unitary: the row space (Gram matrix of columns) is unchanged
         assert np.abs(W[k].conj().T @ W[k] - ref[k].conj().T @ ref[k]).max() < 1e-12 * s_ref[0] ** 2, name
 
