@@ -677,7 +677,7 @@ extern "C" int qsp_overlap(const qsp_c128* a, const int32_t* bonds_a, int D_a, c
   int grid = grid_for(B, 2, d);
   long stride = overlap_work_elems(D_a, D_b);
   if (work_bytes < (size_t)grid * stride * sizeof(cplx)) return QSP_ERR_WORKSPACE;
-  size_t smem = qsp_gemm_smem_bytes(kOverlapNT) + 64;
+  size_t smem = qsp_gemm_smem_bytes(kOverlapNT, QSP_GEMM_TK_DEEP) + 64;  // both products on the FP64 tensor cores (cta_zgemm_deep)
   QSP_LAUNCH(k_overlap, grid, kOverlapNT, smem, (qsp_stream_t)stream, (const cplx*)a, bonds_a, D_a, (const cplx*)b,
              bonds_b, D_b, B, L, (cplx*)result, (cplx*)work, stride);
   ++g_launches;

@@ -344,7 +344,7 @@ __global__ void k_expand_forward(const cplx* __restrict__ in, const int32_t* __r
 // work per CTA: E0, E1 (Da x Db each) and T (Da x 2 Db).
 __host__ __device__ inline long overlap_work_elems(int Da, int Db) { return 2L * Da * Db + 2L * Da * Db + 64; }
 
-__global__ void __launch_bounds__(256) k_overlap(const cplx* __restrict__ a, const int32_t* __restrict__ bonds_a, int Da,
+__global__ void __launch_bounds__(256, 2) k_overlap(const cplx* __restrict__ a, const int32_t* __restrict__ bonds_a, int Da,
                           const cplx* __restrict__ b, const int32_t* __restrict__ bonds_b, int Db, int B, int L,
                           cplx* __restrict__ result, cplx* __restrict__ work, long work_stride) {
   cplx* tiles = (cplx*)QSP_SMEM_BASE();
@@ -368,10 +368,10 @@ __global__ void __launch_bounds__(256) k_overlap(const cplx* __restrict__ a, con
       const cplx* Bi = Bm + (long)i * sb;
       // T[x,(p,y')] = sum_y E[x,y] conj(B[y,p,y'])
       for (int p = 0; p < 2; ++p)
-        cta_zgemm(xa, yb, xb, E, xb, 1, false, Bi + (long)p * Db, 2L * Db, 1, true, T + (long)p * yb, 2L * yb, 1, false,
-                  tiles);
+        cta_zgemm_deep(xa, yb, xb, E, xb, 1, false, Bi + (long)p * Db, 2L * Db, 1, true, T + (long)p * yb, 2L * yb, 1, false,
+                       tiles);
       // E'[x',y'] = sum_{(x,p)} A[x,p,x'] T[(x,p),y']
-      cta_zgemm(ya, yb, 2 * xa, Ai, 1, Da, false, T, yb, 1, false, En, yb, 1, false, tiles);
+      cta_zgemm_deep(ya, yb, 2 * xa, Ai, 1, Da, false, T, yb, 1, false, En, yb, 1, false, tiles);
       cplx* tmp = E;
       E = En;
       En = tmp;
