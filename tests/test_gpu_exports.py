@@ -276,6 +276,42 @@ def test_jacobi_graded_spectrum_vs_lapack(drv, decades):
         assert np.abs(Q @ Q.conj().T - np.eye(n)).max() < 1e-13 * np.sqrt(n) * 8
 
 
+def test_tensor_memory_row_store_experiment_is_bit_identical(drv):
+    """The development-build experiment that keeps 48 of the 64 shared rows of the 128 x 128 Jacobi in tensor memory
+    (tcgen05.ld / st, profiles/r2_tmem_jacobi.md) performs the same arithmetic in the same order as the product's
+    shared-memory variant: identical sweep counts and bit-identical rows."""
+    import ctypes
+
+    import torch
+
+    from qsp_b200 import _runtime
+
+    dev = _runtime.dev_lib()
+    n, B = 128, 5
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    W0 = torch.complex(torch.randn((B, n, n), generator=g, device="cuda", dtype=torch.float64),
+                       torch.randn((B, n, n), generator=g, device="cuda", dtype=torch.float64))
+    W0[1, 3] = W0[1, 2]   # dependent rows
+    W0[2] *= torch.logspace(0, -8, n, dtype=torch.float64, device="cuda")  # graded columns
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    out = []
+    try:
+        for flags in (0, 2):
+            dev.qsp_debug_flags(flags)
+            W = W0.clone()
+            sw = torch.zeros(B, dtype=torch.int32, device="cuda")
+            ok = torch.zeros(B, dtype=torch.int32, device="cuda")
+            dev.qsp_jacobi_bench(p(W), n, n, n, B, 512, p(sw), p(ok), drv.stream)  # (the wrapper raises on an error code)
+            torch.cuda.synchronize()
+            assert int(ok.min()) == 1
+            out.append((W, sw))
+    finally:
+        dev.qsp_debug_flags(0)
+    assert torch.equal(out[0][1], out[1][1])
+    assert torch.equal(torch.view_as_real(out[0][0]), torch.view_as_real(out[1][0]))
+
+
 def test_overlapped_chunks_match_single_call(drv):
     """Engine.seq_prepare splits a batch into chunks that alternate between two streams; HostBatchPipeline streams host
     chunks through the device: both give bit-identical results to one resident call."""
