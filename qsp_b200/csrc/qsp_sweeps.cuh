@@ -57,12 +57,17 @@ __device__ __forceinline__ void qr_make_reflector(cplx* col, int j, int m, int l
     t = cmake(0.0, 0.0);
     bt = alpha.x;
   } else {
-    const double nrm = sqrt(cabs2(alpha) + xn2);
+    // reciprocal square roots instead of sqrt + two divisions: this scalar chain sits on the critical path of the
+    // factorisation (warp 0's look-ahead), and a dependent FP64 operation costs ~13 cycles here
+    const double q = cabs2(alpha) + xn2;
+    const double rq = qsp_rsqrt(q);
+    const double nrm = q * rq;
     bt = alpha.x >= 0.0 ? -nrm : nrm;
-    const double ibt = 1.0 / bt;
+    const double ibt = alpha.x >= 0.0 ? -rq : rq;
     t = cmake((bt - alpha.x) * ibt, -alpha.y * ibt);
     const double dx = alpha.x - bt;                   // |alpha - beta|^2 = dx^2 + alpha.y^2, no cancellation (signs agree)
-    const double id2 = 1.0 / fma(dx, dx, alpha.y * alpha.y);
+    const double rd = qsp_rsqrt(fma(dx, dx, alpha.y * alpha.y));
+    const double id2 = rd * rd;
     const cplx sc = cmake(dx * id2, -alpha.y * id2);  // 1 / (alpha - beta)
     for (int r = j + 1 + lane; r < m; r += 32) col[r] = cmul(col[r], sc);
   }
