@@ -154,9 +154,12 @@ def run_reference(a):
     if rank != 0:
         return
     cores = cpu_cores()
-    steps = max(1, min(a.steps, 3))
     if a.workload == "heisenberg":
         a.L = 32
+    # one untimed warm-up step, then the K steps asked for -- as many of them as fit ~4 minutes of wall clock
+    # (a step = one bounded sample: `cores` instances, constructor pipeline + all layers)
+    t_warm = float(cpu_sample(a.L, a.chi, a.layers, cores, cores, reps=1, workload=a.workload)[0])
+    steps = max(1, min(a.steps, int(240.0 / max(t_warm, 1e-3))))
     walls = cpu_sample(a.L, a.chi, a.layers, cores, cores, reps=steps, workload=a.workload)
     t = float(np.mean(walls))
     v = cores / t
