@@ -132,9 +132,10 @@ struct LCanonPlan {
 static int g_force_big = 0;  // test hook (qsp_debug_flags bit 0): take the large-bond path at any size
 static int g_nt_rc = 0, g_nt_lc = 0;  // tuning hooks: threads per CTA of k_right_compress / k_left_canon (0 = planned)
 static int g_enc_cap = 0;             // test hook: padded bond of the encoded-state buffers (0 = QSP_ENC_CAP)
+static int g_nosort = 0;              // A/B hook (qsp_debug_flags bit 2): no norm ordering of the Jacobi rows
 static int g_tmem = 0;                // experiment (qsp_debug_flags bit 1): qsp_jacobi_bench keeps 128 x 128 rows in tensor memory
 #else
-static const int g_force_big = 0, g_nt_rc = 0, g_nt_lc = 0, g_enc_cap = 0;
+static const int g_force_big = 0, g_nt_rc = 0, g_nt_lc = 0, g_enc_cap = 0, g_nosort = 0;
 #endif
 static bool plan_lcanon(int D, const DevInfo& d, LCanonPlan* p) {
   p->big = false;
@@ -318,6 +319,7 @@ extern "C" int qsp_left_canonize(qsp_c128* mps, int32_t* bonds, int B, int L, in
 extern "C" void qsp_debug_flags(int flags) {
   g_force_big = flags & 1;
   g_tmem = (flags >> 1) & 1;
+  g_nosort = (flags >> 2) & 1;
   g_enc_cap = ((flags >> 4) & 0xf) ? 1 << ((flags >> 4) & 0xf) : 0;  // bits 4..7: log2 of the encoded-state buffer bond
   g_nt_rc = (flags >> 8) & 0xfff;   // bits 8..19: threads per CTA of k_right_compress
   g_nt_lc = (flags >> 20) & 0xfff;  // bits 20..31: threads per CTA of k_left_canon
@@ -557,6 +559,7 @@ static int right_compress_live(const qsp_c128* in, const int32_t* bonds_in, int 
   a.tpp = p.tpp;
   a.max_sweeps = 60;
   a.prof = g_prof;
+  a.presort = g_nosort ? 0 : 1;
   QSP_LAUNCH(k_right_compress, grid, p.nt, p.smem, (qsp_stream_t)stream, a);
   ++g_launches;
   return check_launch();

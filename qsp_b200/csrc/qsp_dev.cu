@@ -70,7 +70,7 @@ extern "C" int qsp_dmma_probe(double* out, int blocks, int threads, int iters, v
 // nrows x ldw matrix (W[B][nrows][ldw]) in place; sweeps[B] receives the sweep counts.
 template <int NTMAX>
 __global__ void __launch_bounds__(NTMAX) k_jacobi_bench(cplx* W, int nrows, int ndotp, int ldw, int B, int cap_elems,
-                                                        int* sweeps, int* ok, int use_tmem) {
+                                                        int* sweeps, int* ok, int use_tmem, int presort) {
   char* sm = QSP_SMEM_BASE();
   cplx* Wsm = (cplx*)sm;
   double* red = (double*)(sm + (size_t)cap_elems * sizeof(cplx));
@@ -83,10 +83,11 @@ __global__ void __launch_bounds__(NTMAX) k_jacobi_bench(cplx* W, int nrows, int 
   JacobiIO io;
   io.src = nullptr;
   io.src_ld = io.src_cols = 0;
-  io.norms_off = -1;
+  io.norms_off = (int)((char*)(red + 64) - sm);  // double[nrows] behind red: scratch of the norm ordering
   io.norms_done = false;
   io.tmem = use_tmem ? *tslot : 0u;
   io.tmem_ok = use_tmem != 0;
+  io.presort = presort != 0;
   for (int inst = blockIdx.x; inst < B; inst += gridDim.x) {
     int ns = 0;
     const double tol = 4e-16 * sqrt((double)ndotp);
@@ -255,19 +256,19 @@ extern "C" void qsp_jacobi_variant(int v) {
 extern "C" int qsp_jacobi_bench(qsp_c128* W, int nrows, int ndotp, int ldw, int B, int nt, int* sweeps, int* ok,
                                 void* stream) {
   DevInfo d = dev_info();
-  long cap = ((long)d.max_smem - 1024) / (long)sizeof(cplx);
+  long cap = ((long)d.max_smem - 4096 - (long)nrows * 8) / (long)sizeof(cplx);
   long need = (long)nrows * ldw;
   if (need < cap) cap = need;
-  size_t smem = (size_t)cap * sizeof(cplx) + 64 * sizeof(double) + 64;
+  size_t smem = (size_t)cap * sizeof(cplx) + (64 + (size_t)nrows + 2) * sizeof(double) + 64;
   int grid = B < d.sms ? B : d.sms;
   if (nt > 512) {
     QSP_PREP_KERNEL(k_jacobi_bench<1024>, smem);
     QSP_LAUNCH(k_jacobi_bench<1024>, grid, nt, smem, (qsp_stream_t)stream, (cplx*)W, nrows, ndotp, ldw, B, (int)cap, sweeps,
-               ok, 0);
+               ok, 0, g_nosort ? 0 : 1);
   } else {
     QSP_PREP_KERNEL(k_jacobi_bench<512>, smem);
     QSP_LAUNCH(k_jacobi_bench<512>, grid, nt, smem, (qsp_stream_t)stream, (cplx*)W, nrows, ndotp, ldw, B, (int)cap, sweeps,
-               ok, g_tmem);
+               ok, g_tmem, g_nosort ? 0 : 1);
   }
   ++g_launches;
   return check_launch();

@@ -292,6 +292,7 @@ struct JacobiIO {
   bool norms_done;
   uint32_t tmem;
   bool tmem_ok;
+  bool presort;  // lay the rows out by decreasing norm before every sweep (uses the norms_off area as scratch)
 };
 
 template <int CPL, int NP, bool HOLD, int TPPC = 0, bool FULL = false, int FASTSEL = -1>
@@ -334,7 +335,80 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
   int sweeps = 0;
   volatile int* flag = (volatile int*)(red + 48);  // set when a rotation above QSP_JAC_QUAD happened
   const int jv = QSP_JV();
+  // Norm ordering: before every sweep the rows are laid out along the line by decreasing norm (a permutation of the
+  // rows: the SVD is unchanged, the row order of the result is whatever the last sweep leaves, as before).  With the
+  // odd-even ordering this takes ~15 % of the sweeps off a full-rank 128 x 128 problem (10.7 -> 9.0) and ~10 % off a
+  // graded one; a sweep costs 128 rounds, the permutation about one (norms, ranks by counting, one trip of the rows
+  // through Wg, which holds nothing the sweeps need).  Needs a double[nrows] scratch: the norms_off area.
+  double* snrm = (io && io->norms_off >= 0 && io->presort) ? (double*)(QSP_SMEM_BASE() + io->norms_off) : nullptr;
   while (sweeps < max_sweeps) {
+    if (snrm) {
+      // squared norms over the Gram columns (scales are 1 here: folded at the end of every sweep)
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        const int p = team * NP + q;
+        double n2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+          if (j < jdot) n2 = fma(R[q][j].x, R[q][j].x, fma(R[q][j].y, R[q][j].y, n2));
+        for (int o = tpp >> 1; o > 0; o >>= 1) n2 += shfl_xor_d(n2, o);
+        if (tl == 0 && p < no) snrm[2 * p + 1] = (n2 == n2) ? n2 : 0.0;
+      }
+      for (int s0 = 0; s0 < ne; s0 += nt / tpp) {  // warp-uniform trip count (shuffles inside)
+        const int slot = s0 + team;
+        const cplx* xr = S + (long)(slot < ne ? slot : 0) * ldw + tl;
+        double n2 = 0.0;
+        for (int j = 0; j < jdot; ++j) {
+          const cplx v = xr[j * tpp];
+          n2 = fma(v.x, v.x, fma(v.y, v.y, n2));
+        }
+        for (int o = tpp >> 1; o > 0; o >>= 1) n2 += shfl_xor_d(n2, o);
+        if (tl == 0 && slot < ne) snrm[2 * slot] = (n2 == n2) ? n2 : 0.0;
+      }
+      __syncthreads();
+      // new position of row i = number of rows ahead of it (larger norm; ties by index): a permutation for any data
+      auto rank_of = [&](int i) {
+        const double ni = snrm[i];
+        int cnt = 0;
+        for (int k = tl; k < nrows; k += tpp) {
+          const double nk = snrm[k];
+          cnt += (nk > ni || (nk == ni && k < i)) ? 1 : 0;
+        }
+        for (int o = tpp >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(QSP_FULL_MASK, cnt, o);
+        return cnt;
+      };
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        const int p = team * NP + q;
+        const int pos = rank_of(p < no ? 2 * p + 1 : 0);
+        if (p < no) {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j)
+            if (j < jlen) Wg[(long)pos * ldw + tl + j * tpp] = R[q][j];
+        }
+      }
+      for (int s0 = 0; s0 < ne; s0 += nt / tpp) {
+        const int slot = s0 + team;
+        const int pos = rank_of(slot < ne ? 2 * slot : 0);
+        if (slot < ne) {
+          const cplx* xr = S + (long)slot * ldw + tl;
+          for (int j = 0; j < jlen; ++j) Wg[(long)pos * ldw + tl + j * tpp] = xr[j * tpp];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        const int p = team * NP + q;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+          if (p < no && j < jlen) R[q][j] = Wg[(long)(2 * p + 1) * ldw + tl + j * tpp];
+      }
+      for (int idx = tid; idx < ne * ldw; idx += nt) {
+        const int r = idx / ldw, c = idx - r * ldw;
+        S[idx] = Wg[(long)(2 * r) * ldw + c];
+      }
+      __syncthreads();
+    }
     if (tid == 0) *flag = 0;
     __syncthreads();
     for (int r = 0; r < nrows; ++r) {

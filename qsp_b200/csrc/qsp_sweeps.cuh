@@ -563,6 +563,7 @@ struct RCompressArgs {
   int tpp;                  // lanes per Jacobi pair
   int max_sweeps;
   long long* prof;          // optional [grid][8] cycle counters (qsp_set_profile_buffer), else null
+  int presort;              // Jacobi rows ordered by norm before every sweep (always on; the development build can switch it off)
 };
 
 // scratch (complex elements per CTA): Mg (Din x 2Dout), Wg (2Dout x (Din+2Dout)),
@@ -786,6 +787,7 @@ __global__ void __launch_bounds__(512) k_right_compress(RCompressArgs P) {
       io.norms_done = false;
       io.tmem = 0u;
       io.tmem_ok = false;
+      io.presort = P.presort != 0;
       if (oe && !modeC) {
         // the register path loads M itself (zero padded on the fly) and leaves s Vh in Wg: no staging copy
         io.src = Mg;

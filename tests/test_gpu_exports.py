@@ -297,7 +297,7 @@ def test_tensor_memory_row_store_experiment_is_bit_identical(drv):
     p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     out = []
     try:
-        for flags in (0, 2):
+        for flags in (4, 6):  # bit 2: no norm ordering (the experiment does not have it), bit 1: rows in tensor memory
             dev.qsp_debug_flags(flags)
             W = W0.clone()
             sw = torch.zeros(B, dtype=torch.int32, device="cuda")
