@@ -33,6 +33,8 @@ thread_local dim3 emu::g_threadIdx, emu::g_blockIdx, emu::g_blockDim, emu::g_gri
 // Per-thread state only (the ABI is re-entrant per host thread and per stream): the last CUDA error string and
 // the optional measurement buffer belong to the calling thread; the launch counter is an atomic tally.
 #include <atomic>
+#include <map>
+#include <mutex>
 static std::atomic<long long> g_launches{0};
 static thread_local long long* g_prof = nullptr;  // optional device buffer [grid][8] for k_right_compress phase cycles
 static thread_local char g_err[256] = "";
@@ -70,8 +72,22 @@ static void dev_fill_nan(qsp_c128* p, long n, qsp_stream_t) {
 static void dev_copy(void* dst, const void* src, size_t bytes, qsp_stream_t) { memcpy(dst, src, bytes); }
 static void dev_zero(void* dst, size_t bytes, qsp_stream_t) { memset(dst, 0, bytes); }
 #else
-#define QSP_PREP_KERNEL(kernel, smem) \
-  cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))
+// The dynamic shared-memory limit of a kernel is one attribute per device, shared by every host thread and stream: it is
+// only ever RAISED (under a lock), so that a launch planned by one thread can never find the limit lowered by another
+// thread that is running the same kernel with a smaller footprint (the two-stream chunk overlap runs two host threads).
+static int prep_kernel(const void* kernel, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> limit;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = limit[std::make_pair(kernel, dev)];
+  if (smem <= cur) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) cur = smem;
+  return (int)e;
+}
+#define QSP_PREP_KERNEL(kernel, smem) prep_kernel((const void*)kernel, (size_t)(smem))
 static int blocks_per_sm(const void* kernel, int nt, size_t smem) {
   int n = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, nt, smem);

@@ -341,7 +341,8 @@ __device__ __noinline__ bool jacobi_rows_oe(cplx* Wg, int nrows, int jdot_, int 
   // (10.7 -> 9.0) and ~30 % fewer on graded ones (18 -> 13 at four decades); a sweep costs 128 rounds, the permutation
   // about one (norms, ranks by counting, one trip of the rows through Wg, which holds nothing the sweeps need).
   // Needs a double[nrows] scratch: the norms_off area.
-  double* snrm = (io && io->norms_off >= 0 && io->presort) ? (double*)(QSP_SMEM_BASE() + io->norms_off) : nullptr;
+  // (not for the few-row problems of the D=2 sweeps: there the permutation costs as much as the sweep)
+  double* snrm = (io && io->norms_off >= 0 && io->presort && nrows >= 16) ? (double*)(QSP_SMEM_BASE() + io->norms_off) : nullptr;
   while (sweeps < max_sweeps) {
     if (snrm) {
       // squared norms over the Gram columns (scales are 1 here: folded at the end of every sweep)
